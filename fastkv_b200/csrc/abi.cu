@@ -1,0 +1,248 @@
+// extern "C" surface of libfastkv_b200.so: argument validation, workspace carving and dispatch.
+// No torch headers, no allocation, no synchronisation (see include/fastkv_b200.h).
+#include <atomic>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace fkv {
+
+int num_sms() {
+  static std::atomic<int> cached{0};
+  int v = cached.load(std::memory_order_relaxed);
+  if (v > 0) return v;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+    (void)cudaGetLastError();
+    return FKV_NUM_SMS_FALLBACK;
+  }
+  cached.store(sms, std::memory_order_relaxed);
+  return sms;
+}
+
+namespace {
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_view(const fkv_view4& v, int es) {
+  if (v.ptr == nullptr) return FKV_EINVAL;
+  if (!aligned16(v.ptr)) return FKV_EALIGN;
+  if ((v.stride_b * es) % 16 || (v.stride_h * es) % 16 || (v.stride_l * es) % 16) return FKV_EALIGN;
+  return FKV_OK;
+}
+
+int selection_heads(const fkv_score_params& p) {
+  return p.mode == FKV_MODE_FASTKV ? p.Hkv : (p.mode == FKV_MODE_SNAPKV ? p.Hq : 1);
+}
+
+int validate_score(const fkv_score_params& p) {
+  if (p.struct_size != sizeof(fkv_score_params)) return FKV_EINVAL;
+  if (p.mode < FKV_MODE_FASTKV || p.mode > FKV_MODE_GEMFILTER) return FKV_EMODE;
+  if (p.impl < FKV_IMPL_AUTO || p.impl > FKV_IMPL_TENSOR) return FKV_EMODE;
+  if (p.dtype < FKV_BF16 || p.dtype > FKV_F32) return FKV_EDTYPE;
+  if (p.D != 64 && p.D != 128) return FKV_EHEADDIM;
+  if (p.B < 1 || p.Hq < 1 || p.Hkv < 1 || p.L < 1 || p.Hq % p.Hkv) return FKV_EINVAL;
+  const int G = p.Hq / p.Hkv;
+  if (G != 1 && G != 2 && G != 4 && G != 8) return FKV_EINVAL;
+  if (p.kernel_size < 1 || p.kernel_size > 63 || (p.kernel_size & 1) == 0) return FKV_EPOOL;
+  if (p.mode != FKV_MODE_GEMFILTER) {
+    if (p.pooling != FKV_POOL_AVG && p.pooling != FKV_POOL_MAX) return FKV_EPOOL;
+    if (p.window_size < 1 || p.window_size > 64 || p.window_size >= p.L) return FKV_EWINDOW;
+    if (p.h0 < 0 || p.h1 <= p.h0 || p.h1 > selection_heads(p)) return FKV_ERANGE;
+  } else {
+    if (p.qh0 < 0 || p.qh1 > p.Hq || (p.qh1 != 0 && p.qh1 <= p.qh0) || (p.qh1 == 0 && p.qh0 != 0)) return FKV_ERANGE;
+  }
+  const int es = dtype_size(p.dtype);
+  int rc;
+  if ((rc = check_view(p.q, es)) != FKV_OK) return rc;
+  if ((rc = check_view(p.k, es)) != FKV_OK) return rc;
+  if (p.score == nullptr) return FKV_EINVAL;
+  if (p.workspace == nullptr ||
+      p.workspace_bytes < score_workspace_bytes(p.mode, p.B, p.Hq, p.Hkv, p.L, p.window_size))
+    return FKV_EWORKSPACE;
+  return FKV_OK;
+}
+
+int run_score(const fkv_score_params& p, cudaStream_t s) {
+  int impl = p.impl;
+  if (impl == FKV_IMPL_AUTO) impl = score_tensor_supported(p) ? FKV_IMPL_TENSOR : FKV_IMPL_SIMPLE;
+  if (impl == FKV_IMPL_TENSOR) {
+    if (!score_tensor_supported(p)) return FKV_EMODE;
+    return launch_score_tensor(p, s);
+  }
+  return launch_score_simple(p, s);
+}
+
+}  // namespace
+}  // namespace fkv
+
+using namespace fkv;
+
+extern "C" {
+
+int fkv_abi_version(void) { return FKV_ABI_VERSION; }
+
+const char* fkv_strerror(int code) {
+  if (code > 0) return cudaGetErrorString((cudaError_t)code);
+  switch (code) {
+    case FKV_OK: return "ok";
+    case FKV_EINVAL: return "invalid argument (null pointer, bad size, struct_size mismatch or head counts)";
+    case FKV_EDTYPE: return "unsupported dtype (bf16, f16, f32 only)";
+    case FKV_EHEADDIM: return "unsupported head_dim (64 or 128 only)";
+    case FKV_EPOOL: return "Pooling method not supported (avgpool/maxpool with an odd kernel_size < 64)";
+    case FKV_ETOPK: return "top-k size out of range (need 1 <= k <= n)";
+    case FKV_EALIGN: return "pointer or stride not 16-byte aligned";
+    case FKV_EWORKSPACE: return "workspace missing or too small (see fkv_workspace_bytes)";
+    case FKV_EMODE: return "unknown or unsupported mode / impl";
+    case FKV_EWINDOW: return "window_size out of range (1..64 and < L)";
+    case FKV_ERANGE: return "head range outside the selection heads";
+  }
+  return "unknown fastkv_b200 error";
+}
+
+size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int32_t L, int32_t window_size,
+                           int32_t capacity, int32_t tsp_k) {
+  const int Hsel = mode == FKV_MODE_FASTKV ? Hkv : (mode == FKV_MODE_SNAPKV ? Hq : 1);
+  size_t b = score_workspace_bytes(mode, B, Hq, Hkv, L, window_size);
+  const int k_head = capacity > window_size ? capacity - window_size : 1;
+  b += topk_workspace_bytes(B * Hsel, L, k_head);
+  if (tsp_k > 0) b += topk_workspace_bytes(B, L, tsp_k);
+  return b + 4096;
+}
+
+size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k) { return topk_workspace_bytes(rows, n, k); }
+
+size_t fkv_decode_workspace_bytes(int32_t B, int32_t Hq, int32_t D, int32_t max_seq_len) {
+  return decode_workspace_bytes(B, Hq, D, max_seq_len);
+}
+
+const char* fkv_score_impl_name(const fkv_score_params* p) {
+  if (!p) return "invalid";
+  if (p->impl == FKV_IMPL_SIMPLE) return "simple";
+  return score_tensor_supported(*p) ? "tensor" : "simple";
+}
+
+int fkv_score(const fkv_score_params* p, void* stream) {
+  if (!p) return FKV_EINVAL;
+  const int rc = validate_score(*p);
+  if (rc != FKV_OK) return rc;
+  return run_score(*p, (cudaStream_t)stream);
+}
+
+int fkv_topk(const fkv_topk_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_topk_params)) return FKV_EINVAL;
+  if (p->rows < 1 || p->n < 1 || !p->src || !p->out || p->tail < 0) return FKV_EINVAL;
+  if (p->k < 1 || p->k > p->n) return FKV_ETOPK;
+  if (p->order != FKV_ORDER_VALUE_DESC && p->order != FKV_ORDER_INDEX_ASC) return FKV_EMODE;
+  return launch_topk(*p, (cudaStream_t)stream);
+}
+
+int fkv_gather_kv(const fkv_gather_kv_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_gather_kv_params)) return FKV_EINVAL;
+  if (p->dtype < FKV_BF16 || p->dtype > FKV_F32) return FKV_EDTYPE;
+  if (p->D != 64 && p->D != 128) return FKV_EHEADDIM;
+  if (p->B < 1 || p->L < 1 || p->n_sel < 0 || p->window_size < 0 || p->h1 <= p->h0 || p->head_div < 1 || !p->idx)
+    return FKV_EINVAL;
+  if (p->window_size > p->L) return FKV_EWINDOW;
+  const int es = dtype_size(p->dtype);
+  int rc;
+  if ((rc = check_view(p->k, es)) || (rc = check_view(p->v, es)) || (rc = check_view(p->k_out, es)) ||
+      (rc = check_view(p->v_out, es)))
+    return rc;
+  return launch_gather_kv(*p, (cudaStream_t)stream);
+}
+
+int fkv_gather_rows(const fkv_gather_rows_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_gather_rows_params)) return FKV_EINVAL;
+  if (p->B < 1 || p->L < 1 || p->T < 1 || !p->src || !p->out || !p->idx) return FKV_EINVAL;
+  if (p->row_bytes < 16 || p->row_bytes % 16 || !aligned16(p->src) || !aligned16(p->out) ||
+      p->src_stride_b_bytes % 16 || p->src_stride_l_bytes % 16 || p->out_stride_b_bytes % 16 || p->out_stride_l_bytes % 16)
+    return FKV_EALIGN;
+  if (p->pos_in && !p->pos_out) return FKV_EINVAL;
+  return launch_gather_rows(*p, (cudaStream_t)stream);
+}
+
+int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_decode_attn_params)) return FKV_EINVAL;
+  if (p->dtype < FKV_BF16 || p->dtype > FKV_F32) return FKV_EDTYPE;
+  if (p->D != 64 && p->D != 128) return FKV_EHEADDIM;
+  if (p->B < 1 || p->Hq < 1 || p->Hkv < 1 || p->Hq % p->Hkv || !p->q || !p->out) return FKV_EINVAL;
+  if (!p->seq_len_dev && p->seq_len < 1) return FKV_EINVAL;
+  const int es = dtype_size(p->dtype);
+  int rc;
+  if ((rc = check_view(p->k_cache, es)) || (rc = check_view(p->v_cache, es))) return rc;
+  if ((p->q_stride_b * es) % 8 || (p->q_stride_h * es) % 8 || (p->out_stride_b * es) % 8 || (p->out_stride_h * es) % 8)
+    return FKV_EALIGN;
+  return launch_decode_attn(*p, (cudaStream_t)stream);
+}
+
+int fkv_cache_append(const fkv_cache_append_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_cache_append_params)) return FKV_EINVAL;
+  if (p->dtype < FKV_BF16 || p->dtype > FKV_F32) return FKV_EDTYPE;
+  if (p->D != 64 && p->D != 128) return FKV_EHEADDIM;
+  if (p->B < 1 || p->Hkv < 1 || p->max_seq_len < 1) return FKV_EINVAL;
+  const int es = dtype_size(p->dtype);
+  int rc;
+  if ((rc = check_view(p->k_new, es)) || (rc = check_view(p->v_new, es)) || (rc = check_view(p->k_cache, es)) ||
+      (rc = check_view(p->v_cache, es)))
+    return rc;
+  return launch_cache_append(*p, (cudaStream_t)stream);
+}
+
+int fkv_compress(const fkv_compress_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_compress_params)) return FKV_EINVAL;
+  const fkv_score_params& sp = p->score;
+  if (sp.mode == FKV_MODE_GEMFILTER) return FKV_EMODE;
+  int rc = validate_score(sp);
+  if (rc != FKV_OK) return rc;
+  const int W = sp.window_size, P = sp.L - W;
+  const int n_sel = p->capacity - W;
+  if (n_sel < 1 || n_sel > P) return FKV_ETOPK;
+  if (p->tsp_k < 0 || p->tsp_k > P) return FKV_ETOPK;
+  if (p->tsp_k > 0 && (!p->tsp_out || sp.mode != FKV_MODE_FASTKV)) return FKV_EINVAL;
+  if (!p->idx_out) return FKV_EINVAL;
+  const int Hsel = sp.h1 - sp.h0;
+  const int es = dtype_size(sp.dtype);
+  if ((rc = check_view(p->v, es)) || (rc = check_view(p->k_out, es)) || (rc = check_view(p->v_out, es))) return rc;
+  // the score call owns the front of the workspace, the top-k calls the rest
+  const size_t score_ws = score_workspace_bytes(sp.mode, sp.B, sp.Hq, sp.Hkv, sp.L, W);
+  const size_t head_ws = topk_workspace_bytes(sp.B * Hsel, P, n_sel);
+  const size_t tsp_ws = p->tsp_k > 0 ? topk_workspace_bytes(sp.B, P, p->tsp_k) : 0;
+  if (sp.workspace_bytes < score_ws + head_ws + tsp_ws) return FKV_EWORKSPACE;
+  char* ws = reinterpret_cast<char*>(sp.workspace);
+  cudaStream_t s = (cudaStream_t)stream;
+
+  if ((rc = run_score(sp, s)) != FKV_OK) return rc;
+
+  // per-head top-k needs rows addressed as one flat list: require the dense [B,Hsel,P] layout
+  if (sp.score_stride_h != P || sp.score_stride_b != (int64_t)Hsel * P) return FKV_EINVAL;
+  fkv_topk_params tk{};
+  tk.struct_size = sizeof(tk);
+  tk.rows = sp.B * Hsel; tk.n = P; tk.k = n_sel; tk.order = FKV_ORDER_VALUE_DESC; tk.tail = 0; tk.nsum = 1;
+  tk.src = sp.score; tk.src_stride_row = P; tk.src_stride_sum = 0;
+  tk.out = p->idx_out; tk.out_stride_row = n_sel;
+  tk.workspace = ws + score_ws; tk.workspace_bytes = head_ws;
+  if ((rc = launch_topk(tk, s)) != FKV_OK) return rc;
+
+  if (p->tsp_k > 0) {
+    fkv_topk_params tt{};
+    tt.struct_size = sizeof(tt);
+    tt.rows = sp.B; tt.n = P; tt.k = p->tsp_k; tt.order = FKV_ORDER_INDEX_ASC; tt.tail = W; tt.nsum = Hsel;
+    tt.src = sp.score; tt.src_stride_row = (int64_t)Hsel * P; tt.src_stride_sum = P;
+    tt.out = p->tsp_out; tt.out_stride_row = p->tsp_k + W;
+    tt.imp_out = p->imp_out;
+    tt.workspace = ws + score_ws + head_ws; tt.workspace_bytes = tsp_ws;
+    if ((rc = launch_topk(tt, s)) != FKV_OK) return rc;
+  }
+
+  fkv_gather_kv_params g{};
+  g.struct_size = sizeof(g);
+  g.dtype = sp.dtype; g.B = sp.B; g.L = sp.L; g.D = sp.D; g.window_size = W; g.n_sel = n_sel;
+  g.h0 = sp.h0; g.h1 = sp.h1; g.head_div = sp.mode == FKV_MODE_SNAPKV ? sp.Hq / sp.Hkv : 1;
+  g.k = sp.k; g.v = p->v; g.idx = p->idx_out; g.idx_stride_b = (int64_t)Hsel * n_sel; g.idx_stride_h = n_sel;
+  g.k_out = p->k_out; g.v_out = p->v_out;
+  return launch_gather_kv(g, s);
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Shared device/host helpers for the fastkv_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <type_traits>
+#include <stdint.h>
+
+#include "../../include/fastkv_b200.h"
+
+#define FKV_NUM_SMS_FALLBACK 148
+
+#define FKV_CUDA_TRY(expr)                      \
+  do {                                          \
+    cudaError_t _e = (expr);                    \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+// Launch check that never synchronises: picks up configuration errors only.
+#define FKV_LAUNCH_CHECK()                      \
+  do {                                          \
+    cudaError_t _e = cudaGetLastError();        \
+    if (_e != cudaSuccess) return (int)_e;      \
+  } while (0)
+
+namespace fkv {
+
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+inline int dtype_size(int dtype) { return dtype == FKV_F32 ? 4 : 2; }
+
+int num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (abi.cu)
+
+// ---- element loads -> fp32 -----------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<__nv_bfloat16> {
+  static constexpr int kPer16B = 8;
+  __device__ static inline void load8(const __nv_bfloat16* p, float* out) {   // 16-byte aligned
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {                    // bf16 -> fp32 is a 16-bit shift
+      out[2 * i] = __uint_as_float(w[i] << 16);
+      out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+};
+template <> struct Elem<__half> {
+  static constexpr int kPer16B = 8;
+  __device__ static inline void load8(const __half* p, float* out) {
+    uint4 raw = *reinterpret_cast<const uint4*>(p);
+    const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 f = __half22float2(h[i]);
+      out[2 * i] = f.x;
+      out[2 * i + 1] = f.y;
+    }
+  }
+};
+template <> struct Elem<float> {
+  static constexpr int kPer16B = 4;
+  __device__ static inline void load8(const float* p, float* out) {
+    float4 a = *reinterpret_cast<const float4*>(p);
+    float4 b = *reinterpret_cast<const float4*>(p + 4);
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+};
+
+// ---- warp / block reductions ---------------------------------------------------------------
+__device__ inline float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ inline float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// 128-bit streaming global accesses (read-once data: keep it out of L1).
+__device__ inline uint4 ld_stream16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ inline void st_stream16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+}  // namespace fkv
+
+// ---- per-file launchers (each .cu implements its own; abi.cu validates and dispatches) -----
+namespace fkv {
+int launch_score_simple(const fkv_score_params& p, cudaStream_t s);
+int launch_score_tensor(const fkv_score_params& p, cudaStream_t s);
+bool score_tensor_supported(const fkv_score_params& p);
+size_t score_workspace_bytes(int mode, int B, int Hq, int Hkv, int L, int W);
+int launch_topk(const fkv_topk_params& p, cudaStream_t s);
+size_t topk_workspace_bytes(int rows, int n, int k);
+int launch_gather_kv(const fkv_gather_kv_params& p, cudaStream_t s);
+int launch_gather_rows(const fkv_gather_rows_params& p, cudaStream_t s);
+int launch_decode_attn(const fkv_decode_attn_params& p, cudaStream_t s);
+int launch_cache_append(const fkv_cache_append_params& p, cudaStream_t s);
+size_t decode_workspace_bytes(int B, int Hq, int D, int max_seq_len);
+}  // namespace fkv

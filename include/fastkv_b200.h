@@ -1,0 +1,224 @@
+/*
+ * fastkv_b200 — C ABI of the B200-native TSP + KV-cache-compression hot path.
+ *
+ * This is the drop-in boundary: every entry point below replaces a stretch of ATen calls in the
+ * reference (dongwonjo/FastKV), cited as file:line relative to the reference tree.  All functions
+ *   - take raw DEVICE pointers, explicit element strides and sizes (no torch types),
+ *   - never allocate, never synchronise, never throw: they only enqueue kernels on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream),
+ *   - return 0 (FKV_OK), a negative FKV_E* argument error, or a positive cudaError_t.
+ * Tensors are "[B,H,L,D] views": element (b,h,l,d) lives at ptr + b*stride_b + h*stride_h +
+ * l*stride_l + d (strides in ELEMENTS, D contiguous), which covers both [B,H,L,D] and the
+ * [B,L,H,D] memory that HF attention layers actually produce.
+ */
+#ifndef FASTKV_B200_H_
+#define FASTKV_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FKV_ABI_VERSION 3
+
+/* ---- enums ------------------------------------------------------------------------------- */
+enum { FKV_BF16 = 0, FKV_F16 = 1, FKV_F32 = 2 };                 /* element type of Q/K/V/hidden   */
+enum { FKV_POOL_AVG = 0, FKV_POOL_MAX = 1 };                     /* 'avgpool' / 'maxpool'          */
+enum { FKV_MODE_FASTKV = 0, FKV_MODE_SNAPKV = 1, FKV_MODE_GEMFILTER = 2 };
+enum { FKV_ORDER_VALUE_DESC = 0, FKV_ORDER_INDEX_ASC = 1 };     /* output order of fkv_topk       */
+enum { FKV_IMPL_AUTO = 0, FKV_IMPL_SIMPLE = 1, FKV_IMPL_TENSOR = 2 };   /* scoring kernel choice  */
+
+enum {
+  FKV_OK = 0,
+  FKV_EINVAL = -1,      /* null pointer / non-positive size / inconsistent head counts            */
+  FKV_EDTYPE = -2,      /* dtype not in {bf16, f16, f32}                                           */
+  FKV_EHEADDIM = -3,    /* head_dim not in {64, 128}                                               */
+  FKV_EPOOL = -4,       /* pooling not avg/max, or kernel_size even / out of range                 */
+  FKV_ETOPK = -5,       /* k < 1 or k > n                                                          */
+  FKV_EALIGN = -6,      /* pointer or stride breaks the 16-byte row alignment the kernels need     */
+  FKV_EWORKSPACE = -7,  /* workspace missing or smaller than fkv_workspace_bytes()                 */
+  FKV_EMODE = -8,       /* unknown mode / impl, or combination not supported                       */
+  FKV_EWINDOW = -9,     /* window_size < 1, > 64, or >= L                                          */
+  FKV_ERANGE = -10      /* head range [h0,h1) outside the selection heads                          */
+};
+
+/* ---- tensor view ------------------------------------------------------------------------- */
+typedef struct fkv_view4 {          /* [B,H,L,D] view, D contiguous; strides in elements          */
+  const void* ptr;
+  int64_t stride_b, stride_h, stride_l;
+} fkv_view4;
+
+/* ---- K1 + K2: observation-window scoring, pooling, GQA group-sum ------------------------ */
+/*
+ * Replaces baselines/fastkv/utils.py:93-112 (repeat_kv, matmul, mask, softmax, window row-sum,
+ * avg/max_pool1d, group-sum), baselines/snapkv/utils.py:72-87 (same without the group-sum, one
+ * selection head per query head) and baselines/gemfilter/utils.py:25-33 (last-row raw dot
+ * products, sum over query heads, avg_pool1d).
+ *
+ * "Selection heads": FASTKV -> the Hkv kv heads; SNAPKV -> the Hq query heads (K of query head
+ * hq is kv head hq / (Hq/Hkv)); GEMFILTER -> one virtual head 0 that sums the query heads in
+ * [qh0,qh1) (used for head sharding; default all).  The call computes selection heads [h0,h1).
+ *
+ * Output: score[b, h-h0, j] fp32 for j in [0, P), P = L - W (GEMFILTER: P = L), laid out with
+ * score_stride_b / score_stride_h (elements).
+ */
+typedef struct fkv_score_params {
+  uint32_t struct_size;             /* sizeof(fkv_score_params), ABI guard                        */
+  int32_t mode, dtype, impl;
+  int32_t B, Hq, Hkv, L, D;
+  int32_t window_size, kernel_size, pooling;
+  int32_t h0, h1;                   /* selection-head range computed by this call                 */
+  int32_t qh0, qh1;                 /* GEMFILTER only: query heads summed; 0,0 = all              */
+  fkv_view4 q;                      /* [B,Hq,L,D]                                                 */
+  fkv_view4 k;                      /* [B,Hkv,L,D]                                                */
+  float* score;                     /* [B,h1-h0,P]                                                */
+  int64_t score_stride_b, score_stride_h;
+  void* workspace;
+  size_t workspace_bytes;
+} fkv_score_params;
+
+int fkv_score(const fkv_score_params* p, void* stream);
+
+/* ---- K3: deterministic top-k ------------------------------------------------------------- */
+/*
+ * Replaces Tensor.topk at baselines/fastkv/utils.py:113 (per head, order VALUE_DESC) and the
+ * sum(dim=-2) + topk + arange/cat + sort chain at :127-130 (TSP, order INDEX_ASC with
+ * `tail` = W trailing window indices appended), also gemfilter/utils.py:34 + :60.
+ *
+ * Row r, element j is   sum_{s < nsum} src[r*src_stride_row + s*src_stride_sum + j]   (summed in
+ * increasing s: the fixed-order TSP head-sum of :127; nsum = 1 for a plain row).
+ * Total order: value descending, then index ascending (the reference's tie order is unspecified).
+ * Output out[r*out_stride_row + i], i < k, then `tail` extra entries n, n+1, .. n+tail-1.
+ * If `imp_out` is non-NULL and nsum > 1 the summed row is also written there ([rows,n] dense).
+ */
+typedef struct fkv_topk_params {
+  uint32_t struct_size;
+  int32_t rows, n, k, order, tail, nsum;
+  const float* src;
+  int64_t src_stride_row, src_stride_sum;
+  int64_t* out;
+  int64_t out_stride_row;
+  float* imp_out;
+  void* workspace;
+  size_t workspace_bytes;
+} fkv_topk_params;
+
+int fkv_topk(const fkv_topk_params* p, void* stream);
+
+/* ---- K4: KV compaction ------------------------------------------------------------------- */
+/*
+ * Replaces the expand + 2x gather + 2x cat at baselines/fastkv/utils.py:114-121 (and the SnapKV
+ * twin snapkv/utils.py:88-101).  For selection head h in [h0,h1):
+ *   out[b,h-h0,i,:]        = src[b, h / head_div, idx[b,h-h0,i], :]      i < n_sel
+ *   out[b,h-h0,n_sel+r,:]  = src[b, h / head_div, L-W+r, :]              r < W
+ * for src in {k, v}.  Outputs are [B,h1-h0,*,D] views (stride_l = D normally) so they can be a
+ * slice of a pre-allocated cache.  head_div = 1 (FASTKV) or Hq/Hkv (SNAPKV).  Bit-exact copy.
+ */
+typedef struct fkv_gather_kv_params {
+  uint32_t struct_size;
+  int32_t dtype, B, L, D, window_size, n_sel, h0, h1, head_div;
+  fkv_view4 k, v;
+  const int64_t* idx;               /* [B,h1-h0,n_sel]                                            */
+  int64_t idx_stride_b, idx_stride_h;
+  fkv_view4 k_out, v_out;           /* writable; [B,h1-h0,n_sel+W,D]                              */
+} fkv_gather_kv_params;
+
+int fkv_gather_kv(const fkv_gather_kv_params* p, void* stream);
+
+/* ---- K4b: hidden-state / position-id propagation ---------------------------------------- */
+/*
+ * Replaces the two torch.gather calls at baselines/fastkv/llama_model.py:255-257 (Mistral
+ * mistral_model.py:220-222):  out[b,i,:] = src[b, idx[b,i], :]  (row_bytes per row, multiple of
+ * 16) and, when pos_in != NULL, pos_out[b,i] = pos_in[b*pos_stride_b + idx[b,i]] (int64;
+ * pos_stride_b = 0 broadcasts a [1,L] position_ids).  Bit-exact copy.
+ */
+typedef struct fkv_gather_rows_params {
+  uint32_t struct_size;
+  int32_t B, L, T;
+  int64_t row_bytes;
+  const void* src;   int64_t src_stride_b_bytes, src_stride_l_bytes;
+  void* out;         int64_t out_stride_b_bytes, out_stride_l_bytes;
+  const int64_t* idx; int64_t idx_stride_b;
+  const int64_t* pos_in; int64_t pos_stride_b;
+  int64_t* pos_out;  int64_t pos_out_stride_b;
+} fkv_gather_rows_params;
+
+int fkv_gather_rows(const fkv_gather_rows_params* p, void* stream);
+
+/* ---- K5: split-K decode attention over the compact cache --------------------------------- */
+/*
+ * Replaces flash_attn_func at q_len == 1 (baselines/fastkv/llama_model.py:79-81 via :181-183;
+ * mistral_model.py:143-153): out[b,hq,:] = softmax(q[b,hq,:] . K[b,hq/G,0:S,:]^T * scale) V.
+ * q/out are [B,Hq,D] with stride_b / stride_h (elements); caches are [B,Hkv,S_max,D] views.
+ * S is `seq_len`, or *seq_len_dev (int32 on device, read by the kernel) when that is non-NULL so
+ * a captured CUDA graph can be replayed while the cache grows.
+ */
+typedef struct fkv_decode_attn_params {
+  uint32_t struct_size;
+  int32_t dtype, B, Hq, Hkv, D, seq_len, max_seq_len, num_splits;   /* num_splits 0 = auto      */
+  float scale;                                                       /* 0 = 1/sqrt(D)            */
+  const void* q;  int64_t q_stride_b, q_stride_h;
+  fkv_view4 k_cache, v_cache;
+  void* out;      int64_t out_stride_b, out_stride_h;
+  const int32_t* seq_len_dev;
+  void* workspace;
+  size_t workspace_bytes;
+} fkv_decode_attn_params;
+
+int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream);
+
+/*
+ * Appends one new K/V row per (b, kv head) at row *seq_len_dev (or seq_len) of the cache and,
+ * if bump != 0, increments *seq_len_dev afterwards (replaces DynamicCache.update's torch.cat at
+ * baselines/fastkv/llama_model.py:144).  k_new/v_new are [B,Hkv,1,D] views.
+ */
+typedef struct fkv_cache_append_params {
+  uint32_t struct_size;
+  int32_t dtype, B, Hkv, D, seq_len, max_seq_len, bump;
+  fkv_view4 k_new, v_new;
+  fkv_view4 k_cache, v_cache;       /* writable                                                   */
+  int32_t* seq_len_dev;
+} fkv_cache_append_params;
+
+int fkv_cache_append(const fkv_cache_append_params* p, void* stream);
+
+/* ---- fused chain: one host call for update_kv -------------------------------------------- */
+/*
+ * score -> per-head top-k -> KV compaction [-> TSP top-k], i.e. the whole of
+ * FastKVCluster.update_kv (baselines/fastkv/utils.py:93-130) or SnapKVCluster.update_kv
+ * (baselines/snapkv/utils.py:72-101) behind one call, for selection heads [h0,h1).
+ * tsp_k > 0 additionally emits tsp_out[b, 0:tsp_k+W] (ascending) from the sum over the heads
+ * computed by THIS call (single-GPU case; multi-GPU callers exchange `score` first and call
+ * fkv_topk themselves).
+ */
+typedef struct fkv_compress_params {
+  uint32_t struct_size;
+  fkv_score_params score;           /* score.score / workspace as for fkv_score                   */
+  int32_t capacity;                 /* C: rows kept per head including the W window rows          */
+  int32_t tsp_k;                    /* T - W, or 0                                                */
+  fkv_view4 v;                      /* [B,Hkv,L,D]                                                */
+  int64_t* idx_out;                 /* [B,h1-h0,C-W]                                              */
+  fkv_view4 k_out, v_out;           /* [B,h1-h0,C,D]                                              */
+  int64_t* tsp_out;                 /* [B,T] or NULL                                              */
+  float* imp_out;                   /* [B,P] or NULL                                              */
+} fkv_compress_params;
+
+int fkv_compress(const fkv_compress_params* p, void* stream);
+
+/* ---- queries ----------------------------------------------------------------------------- */
+/* Bytes of scratch fkv_score / fkv_topk / fkv_compress need for these sizes (upper bound).     */
+size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int32_t L, int32_t window_size,
+                           int32_t capacity, int32_t tsp_k);
+size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k);
+size_t fkv_decode_workspace_bytes(int32_t B, int32_t Hq, int32_t D, int32_t max_seq_len);
+const char* fkv_strerror(int code);
+int fkv_abi_version(void);
+/* Name of the scoring kernel that FKV_IMPL_AUTO picks for these parameters ("simple"/"tensor"). */
+const char* fkv_score_impl_name(const fkv_score_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTKV_B200_H_ */

@@ -1,0 +1,120 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol
+include/fastkv_b200.h declares; host-side control flow that needs no kernel."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fastkv_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fkv_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fastkv_b200 import _lib
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 12
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/fastkv_b200.h but not exported"
+    assert set(_lib.EXPORTS) == set(names)
+    assert lib.fkv_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_sizes_match_c_layout():
+    """ctypes mirrors must have the C sizes (checked against sizes compiled from the header)."""
+    import subprocess, tempfile
+    from fastkv_b200 import _lib
+    src = '#include <stdio.h>\n#include "fastkv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(fkv_view4),sizeof(fkv_score_params),sizeof(fkv_topk_params),sizeof(fkv_gather_kv_params),' \
+          'sizeof(fkv_gather_rows_params),sizeof(fkv_decode_attn_params),sizeof(fkv_cache_append_params),' \
+          'sizeof(fkv_compress_params));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    mirrors = [_lib.View4, _lib.ScoreParams, _lib.TopkParams, _lib.GatherKvParams, _lib.GatherRowsParams,
+               _lib.DecodeAttnParams, _lib.CacheAppendParams, _lib.CompressParams]
+    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+
+
+def test_strerror_and_error_mapping():
+    from fastkv_b200 import _lib
+    lib = _lib.load()
+    assert b"Pooling method not supported" in lib.fkv_strerror(_lib.EPOOL)
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        _lib.check(_lib.EPOOL)
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        _lib.pool_code("minpool")
+    with pytest.raises(RuntimeError):
+        _lib.check(2)          # cudaErrorMemoryAllocation
+
+
+def test_null_and_bad_arguments_return_codes_without_a_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on the CPU box."""
+    from fastkv_b200 import _lib
+    lib = _lib.load()
+    assert lib.fkv_score(None, None) == -1
+    p = _lib.TopkParams()
+    p.struct_size = ctypes.sizeof(_lib.TopkParams)
+    p.rows, p.n, p.k = 1, 8, 9
+    p.src, p.out = 16, 16
+    assert lib.fkv_topk(ctypes.byref(p), None) == -5           # k > n
+    p.struct_size = 4
+    assert lib.fkv_topk(ctypes.byref(p), None) == -1
+    sp = _lib.ScoreParams()
+    sp.struct_size = ctypes.sizeof(_lib.ScoreParams)
+    sp.B, sp.Hq, sp.Hkv, sp.L, sp.D = 1, 8, 2, 64, 96
+    assert lib.fkv_score(ctypes.byref(sp), None) == -3          # head_dim 96
+    sp.D, sp.kernel_size = 128, 4
+    assert lib.fkv_score(ctypes.byref(sp), None) == -4          # even kernel_size
+    assert lib.fkv_workspace_bytes(0, 1, 32, 8, 32768, 8, 2048, 2040) > 0
+
+
+def test_early_return_is_by_reference_and_needs_no_gpu():
+    """baselines/fastkv/utils.py:89-91: q_len < max_capacity_prompt returns the inputs themselves."""
+    from fastkv_b200 import FastKVCluster, SnapKVCluster
+    k, v = torch.randn(1, 2, 64, 128), torch.randn(1, 2, 64, 128)
+    q = torch.randn(1, 8, 64, 128)
+    cl = FastKVCluster(max_capacity_prompt=128, tsp_layer=True, tsp_length=32)
+    ko, vo, tsp = cl.update_kv(k, q, v, None, 4, 0)
+    assert ko is k and vo is v and tsp is None
+    sn = SnapKVCluster(window_size=8, max_capacity_prompt=128)
+    ko, vo = sn.update_kv(k, q, v, None, 4)
+    assert ko is k and vo is v
+
+
+def test_proportional_mode_rewrites_attributes_like_the_reference():
+    """utils.py:86-87: proportional mode overwrites self.max_capacity_prompt with int(q_len * retain_rate)."""
+    from fastkv_b200 import FastKVCluster
+    cl = FastKVCluster(window_size=8, max_capacity_prompt=512, retain_rate=2.0, eviction_mode="proportional")
+    k, v, q = torch.randn(1, 2, 50, 128), torch.randn(1, 2, 50, 128), torch.randn(1, 8, 50, 128)
+    ko, vo, tsp = cl.update_kv(k, q, v, None, 4, 0)          # C = 100 > q_len -> early return
+    assert cl.max_capacity_prompt == 100 and ko is k and tsp is None
+
+
+def test_no_cpu_fallback():
+    from fastkv_b200 import FastKVCluster
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    cl = FastKVCluster(window_size=8, max_capacity_prompt=16)
+    k, v, q = torch.randn(1, 2, 64, 128), torch.randn(1, 2, 64, 128), torch.randn(1, 8, 64, 128)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cl.update_kv(k, q, v, None, 4, 0)
+
+
+def test_constructor_assert_and_reset_semantics():
+    from fastkv_b200 import FastKVCluster
+    with pytest.raises(AssertionError):
+        FastKVCluster(window_size=8, max_capacity_prompt=8)      # utils.py:54
+    cl = FastKVCluster()
+    cl.reset(tsp_length=1024)
+    assert cl.tsp_length == 1024          # not the reference's accidental 1-tuple (utils.py:73)

@@ -1,0 +1,372 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Protocol (SURVEY.md §8c / BASELINE.json north_star): inputs hold bf16-representable values; the
+oracle sees them as fp32, the kernels as bf16 (tensor path) or fp32 (simple path).
+  * selected index sets equal the oracle's except where the oracle's own score gap to its k-th
+    score is < 1e-5 relative (near ties);
+  * compacted K/V and propagated hidden rows are bit-exact given OUR indices;
+  * scores within rtol 2e-5 of the oracle's fp32 scores (fp32 accumulation-order noise).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import fastkv_oracle as O
+from conftest import golden_names, load_golden, full_query
+from parity_utils import (make_inputs, check_selection, check_scores_close, check_compaction_exact,
+                          check_topk_consistent, check_tsp_consistent)
+
+pytestmark = pytest.mark.gpu
+SCORE_RTOL = 2e-5
+DEV = "cuda"
+
+
+def _lib():
+    from fastkv_b200 import _lib as L
+    return L
+
+
+def _run_cluster(fx_knobs, k, q, v, groups, impl):
+    from fastkv_b200 import FastKVCluster
+    cl = FastKVCluster(**fx_knobs)
+    cl.keep_aux = True
+    cl.score_impl = impl
+    out = cl.update_kv(k, q, v, None, groups, 0)
+    torch.cuda.synchronize()
+    return cl, out
+
+
+def _impls_for(dtype):
+    L = _lib()
+    lib = L.load()
+    impls = [L.IMPL_SIMPLE]
+    # the tensor-core path exists for 16-bit inputs only; exercise it whenever AUTO would pick it
+    if dtype != torch.float32:
+        impls.append(L.IMPL_AUTO)
+    return impls
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures (outputs of the unmodified reference)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("name", [n for n in golden_names("fastkv") if n != "fastkv_bf16_run"])
+def test_fastkv_matches_reference_golden(name, dtype):
+    fx = load_golden(name)
+    sh, knobs = fx["shape"], fx["knobs"]
+    l, g, w = sh["L"], sh["Hq"] // sh["Hkv"], knobs["window_size"]
+    k32, v32, q32 = fx["k"].float(), fx["v"].float(), full_query(fx["q_window"], l).float()
+    ref = O.fastkv_update_kv(k32, q32, v32, g, **knobs)                  # == reference (pinned on CPU)
+    for impl in _impls_for(dtype):
+        cl, (ko, vo, tsp) = _run_cluster(knobs, k32.to(DEV, dtype), q32.to(DEV, dtype), v32.to(DEV, dtype), g, impl)
+        assert cl.max_capacity_prompt == fx["capacity_after"]
+        if ref.skipped:
+            assert tsp is None and ko.shape == k32.shape
+            continue
+        aux = cl.last_aux
+        c = ref.capacity
+        assert ko.shape == (sh["B"], sh["Hkv"], c, sh["D"]) and ko.dtype == dtype
+        check_scores_close(ref.score, aux["score"], SCORE_RTOL, f"{name}/{impl}")
+        if fx["dist"] == "ties" or knobs["pooling"] == "maxpool":
+            # exact ties: tie order is unspecified upstream -> compare the selected score multisets
+            ours = torch.gather(ref.score, -1, aux["idx"].cpu()).sort(-1).values
+            theirs = torch.gather(ref.score, -1, ref.idx).sort(-1).values
+            assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+        else:
+            flat = ref.score.reshape(-1, ref.score.shape[-1])
+            check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), name)
+            # golden K/V: same rows as the reference wherever the index sets agree exactly
+            if torch.equal(aux["idx"].cpu(), ref.idx):
+                assert torch.equal(ko.cpu().to(torch.bfloat16), fx["key_out"])
+                assert torch.equal(vo.cpu().to(torch.bfloat16), fx["value_out"])
+        check_topk_consistent(aux["score"], aux["idx"], name)
+        check_compaction_exact(k32.to(dtype), v32.to(dtype), aux["idx"], ko, vo, w)
+        if ref.tsp_idx is None:
+            assert tsp is None
+        else:
+            assert tsp.shape == ref.tsp_idx.shape and tsp.dtype == torch.int64
+            check_tsp_consistent(aux["importance"], tsp, w, name)
+            if fx["dist"] == "ties" or knobs["pooling"] == "maxpool":
+                ours = torch.gather(ref.importance, -1, tsp.cpu()[:, :-w]).sort(-1).values
+                theirs = torch.gather(ref.importance, -1, ref.tsp_idx[:, :-w]).sort(-1).values
+                assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+            else:
+                check_selection(ref.importance, ref.tsp_idx[:, :-w], tsp[:, :-w], name + "/tsp")
+                if torch.equal(tsp.cpu(), ref.tsp_idx):
+                    assert torch.equal(tsp.cpu(), fx["tsp_idx"])
+
+
+def test_bf16_run_of_the_reference_is_within_bf16_tolerance():
+    """Informational leg of the protocol: the reference run in bf16 rounds probabilities to bf16
+    (utils.py:103); our fp32 scores must agree with it to bf16 precision on the kept mass."""
+    fx = load_golden("fastkv_bf16_run")
+    sh, knobs = fx["shape"], fx["knobs"]
+    l, g = sh["L"], sh["Hq"] // sh["Hkv"]
+    k, v, q = fx["k"], fx["v"], full_query(fx["q_window"], l)
+    ref = O.fastkv_update_kv(k, q, v, g, **knobs)                         # bf16 arithmetic like the reference
+    cl, _ = _run_cluster(knobs, k.to(DEV), q.to(DEV), v.to(DEV), g, _lib().IMPL_AUTO)
+    got = cl.last_aux["score"].cpu()
+    rel = ((got - ref.score.float()).abs() / ref.score.float().abs().clamp_min(1e-6)).median().item()
+    assert rel < 2e-2, rel                                                # bf16 has 8 bits of mantissa
+    overlap = len(set(cl.last_aux["idx"][0, 0].tolist()) & set(ref.idx[0, 0].tolist())) / ref.idx.shape[-1]
+    assert overlap > 0.8, overlap
+
+
+@pytest.mark.parametrize("name", golden_names("snapkv"))
+@pytest.mark.parametrize("expanded", [True, False])
+def test_snapkv_matches_reference_golden(name, expanded):
+    from fastkv_b200 import SnapKVCluster
+    fx = load_golden(name)
+    sh, knobs = fx["shape"], fx["knobs"]
+    l, g, w = sh["L"], sh["Hq"] // sh["Hkv"], knobs["window_size"]
+    k32, v32, q32 = fx["k"].float(), fx["v"].float(), full_query(fx["q_window"], l).float()
+    ref = O.snapkv_update_kv(O.expand_kv_heads(k32, g), q32, O.expand_kv_heads(v32, g), **knobs)
+    kin, vin = (O.expand_kv_heads(k32, g), O.expand_kv_heads(v32, g)) if expanded else (k32, v32)
+    cl = SnapKVCluster(**knobs)
+    cl.keep_aux = True
+    ko, vo = cl.update_kv(kin.to(DEV, torch.bfloat16), q32.to(DEV, torch.bfloat16), vin.to(DEV, torch.bfloat16), None, g)
+    torch.cuda.synchronize()
+    aux = cl.last_aux
+    assert ko.shape == (sh["B"], sh["Hq"], ref.capacity, sh["D"])
+    check_scores_close(ref.score, aux["score"], SCORE_RTOL, name)
+    check_topk_consistent(aux["score"], aux["idx"], name)
+    check_compaction_exact(k32.bfloat16(), v32.bfloat16(), aux["idx"], ko, vo, w, head_div=g)
+    if knobs["pooling"] == "avgpool":
+        flat = ref.score.reshape(-1, ref.score.shape[-1])
+        check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), name)
+        if torch.equal(aux["idx"].cpu(), ref.idx):
+            assert torch.equal(ko.cpu(), fx["key_out"]) and torch.equal(vo.cpu(), fx["value_out"])
+
+
+@pytest.mark.parametrize("name", golden_names("gemfilter"))
+def test_gemfilter_matches_reference_golden(name):
+    import types
+    from fastkv_b200 import find_context
+    fx = load_golden(name)
+    sh = fx["shape"]
+    n, g = sh["L"], sh["Hq"] // sh["Hkv"]
+    q32, k32 = full_query(fx["q_window"], n).float(), fx["k"].float()
+    ref_scores, ref_idx, ref_sorted = O.gemfilter_select(q32, k32, g, fx["topk"])
+    holder = types.SimpleNamespace(eviction_mode="constant", retain_rate=0.1, topk=fx["topk"], indecies=None,
+                                   layer_idx=13, select_layer_idx=13, num_key_value_groups=g)
+    find_context(holder, q32.to(DEV, torch.bfloat16), k32.to(DEV, torch.bfloat16))
+    torch.cuda.synchronize()
+    got = holder.indecies
+    assert got.shape == ref_idx.shape
+    check_selection(ref_scores[0], ref_idx[0], got[0], name)
+    if set(got[0, 0].tolist()) == set(ref_idx[0, 0].tolist()):
+        assert torch.equal(torch.sort(got[0, 0].cpu()).values, fx["sorted_indices"])
+
+
+# ---------------------------------------------------------------------------------------------
+# seeded inputs against the oracle at sizes it finishes in seconds
+# ---------------------------------------------------------------------------------------------
+CASES = [
+    # b, hq, hkv, L, D, W, ks, pooling, C, T, dist
+    (1, 32, 8, 8192, 128, 8, 7, "avgpool", 512, 2048, "gauss"),        # BASELINE config 1 shape
+    (1, 32, 8, 4099, 128, 8, 7, "avgpool", 256, 1024, "peaky"),        # ragged length
+    (2, 16, 4, 2048, 128, 16, 5, "avgpool", 128, 512, "gauss"),        # batch 2, W=16
+    (1, 32, 8, 3000, 128, 32, 13, "avgpool", 300, 600, "peaky"),       # W=32, kernel 13
+    (1, 8, 8, 1500, 64, 8, 7, "avgpool", 100, 200, "gauss"),           # MHA (G=1), D=64
+    (1, 16, 2, 1024, 128, 8, 7, "maxpool", 128, 256, "gauss"),         # G=8, maxpool
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+@pytest.mark.parametrize("case", CASES, ids=[f"L{c[3]}_W{c[5]}_k{c[6]}_{c[7]}_C{c[8]}" for c in CASES])
+def test_fastkv_seeded_vs_oracle(case, dtype):
+    b, hq, hkv, l, d, w, ks, pooling, c, t, dist = case
+    g = hq // hkv
+    q, k, v = make_inputs(100 + l, b, hq, hkv, l, d, dtype=torch.float32, dist=dist)
+    if dtype == torch.float16:                       # keep values fp16-representable too
+        q, k, v = [x.clamp(-8, 8) for x in (q, k, v)]
+    knobs = dict(window_size=w, max_capacity_prompt=c, kernel_size=ks, pooling=pooling, tsp_layer=True, tsp_length=t)
+    ref = O.fastkv_update_kv(k, q, v, g, **knobs)
+    for impl in _impls_for(dtype):
+        cl, (ko, vo, tsp) = _run_cluster(knobs, k.to(DEV, dtype), q.to(DEV, dtype), v.to(DEV, dtype), g, impl)
+        aux = cl.last_aux
+        err = check_scores_close(ref.score, aux["score"], SCORE_RTOL, f"impl {impl}")
+        check_topk_consistent(aux["score"], aux["idx"])
+        check_tsp_consistent(aux["importance"], tsp, w)
+        check_compaction_exact(k.to(dtype), v.to(dtype), aux["idx"], ko, vo, w)
+        assert not ko.data_ptr() == k.data_ptr()
+        if pooling == "avgpool":
+            flat = ref.score.reshape(-1, ref.score.shape[-1])
+            check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), f"impl {impl}")
+            check_selection(ref.importance, ref.tsp_idx[:, :-w], tsp[:, :-w], "tsp")
+        else:
+            ours = torch.gather(ref.score, -1, aux["idx"].cpu()).sort(-1).values
+            theirs = torch.gather(ref.score, -1, ref.idx).sort(-1).values
+            assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+
+
+def test_strided_blhd_views_equal_contiguous_inputs():
+    """update_kv gets [B,H,L,D] views of [B,L,H,D] memory; results must not depend on the layout."""
+    knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)
+    q, k, v = [x.to(DEV) for x in make_inputs(7, 2, 32, 8, 1536, 128, layout="blhd")]
+    assert not k.is_contiguous()
+    _, a = _run_cluster(knobs, k, q, v, 4, _lib().IMPL_AUTO)
+    _, b = _run_cluster(knobs, k.contiguous(), q.contiguous(), v.contiguous(), 4, _lib().IMPL_AUTO)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+
+
+def test_simple_and_auto_paths_select_identically_on_clear_gaps():
+    L = _lib()
+    knobs = dict(window_size=8, max_capacity_prompt=256, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=512)
+    q, k, v = [x.to(DEV) for x in make_inputs(11, 1, 32, 8, 4096, 128, dist="peaky")]
+    ca, _ = _run_cluster(knobs, k, q, v, 4, L.IMPL_SIMPLE)
+    cb, _ = _run_cluster(knobs, k, q, v, 4, L.IMPL_AUTO)
+    check_scores_close(ca.last_aux["score"], cb.last_aux["score"], SCORE_RTOL)
+    sa = ca.last_aux["score"].reshape(-1, ca.last_aux["score"].shape[-1])
+    check_selection(sa, ca.last_aux["idx"].reshape(sa.shape[0], -1), cb.last_aux["idx"].reshape(sa.shape[0], -1))
+
+
+# ---------------------------------------------------------------------------------------------
+# full BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("l,c,t,b", [(32768, 2048, 2048, 1), (131072, 2048, 2048, 1), (32768, 512, 2048, 2)])
+def test_full_size_properties(l, c, t, b):
+    hq, hkv, d, w = 32, 8, 128, 8
+    g = torch.Generator(device=DEV).manual_seed(l + c)
+    q = torch.randn(b, l, hq, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
+    k = torch.randn(b, l, hkv, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
+    v = torch.randn(b, l, hkv, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
+    knobs = dict(window_size=w, max_capacity_prompt=c, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=t)
+    cl, (ko, vo, tsp) = _run_cluster(knobs, k, q, v, hq // hkv, _lib().IMPL_AUTO)
+    aux = cl.last_aux
+    score = aux["score"]
+    assert score.shape == (b, hkv, l - w) and torch.isfinite(score).all() and (score >= 0).all()
+    # softmax rows sum to 1: total vote mass over the prefix is <= W per query head, pooled mass likewise
+    assert (score.sum(-1) <= (hq // hkv) * w * (1 + 1e-3)).all()
+    check_topk_consistent(score, aux["idx"])
+    check_tsp_consistent(aux["importance"], tsp, w)
+    imp = score.sum(dim=1)
+    assert torch.allclose(imp, aux["importance"], rtol=1e-5, atol=0)
+    check_compaction_exact(k, v, aux["idx"], ko, vo, w)
+    assert (tsp[:, 1:] > tsp[:, :-1]).all() and tsp[:, -1].eq(l - 1).all()
+    # idempotence of the propagation: gathering with the TSP set keeps the window rows last
+    from fastkv_b200 import ops
+    hidden = torch.randn(b, l, 4096, generator=g, device=DEV, dtype=torch.bfloat16)
+    pos = torch.arange(l, device=DEV).unsqueeze(0)
+    nh, npos = ops.gather_rows(hidden, tsp, pos)
+    assert torch.equal(npos, tsp)
+    assert torch.equal(nh, torch.gather(hidden, 1, tsp.unsqueeze(-1).expand(-1, -1, 4096)))
+
+
+def test_len_equal_capacity_reorders_everything():
+    """q_len == C still runs the selection over all L-W prefix tokens (strict '<', utils.py:89)."""
+    knobs = dict(window_size=8, max_capacity_prompt=2048, kernel_size=7, pooling="avgpool", tsp_layer=False)
+    q, k, v = [x.to(DEV) for x in make_inputs(5, 1, 32, 8, 2048, 128)]
+    cl, (ko, vo, tsp) = _run_cluster(knobs, k, q, v, 4, _lib().IMPL_AUTO)
+    assert tsp is None and ko.shape == (1, 8, 2048, 128)
+    idx = cl.last_aux["idx"]
+    assert torch.equal(idx.sort(-1).values, torch.arange(2040, device=DEV).expand(1, 8, -1))
+    check_compaction_exact(k, v, idx, ko, vo, 8)
+
+
+# ---------------------------------------------------------------------------------------------
+# individual kernels
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,k", [(1, 1), (7, 7), (1000, 1), (1000, 999), (4096, 512), (32760, 2040), (131064, 2040),
+                                 (131064, 13099), (50000, 20000)])
+def test_topk_kernel_is_exact(n, k):
+    from fastkv_b200 import ops
+    L = _lib()
+    g = torch.Generator().manual_seed(n * 7 + k)
+    rows = torch.stack([
+        torch.rand(n, generator=g),                                    # positive, continuous
+        torch.randn(n, generator=g),                                   # signed
+        torch.randint(0, 5, (n,), generator=g).float(),                # heavy exact ties
+        torch.zeros(n),                                                # all equal
+        torch.rand(n, generator=g).pow(8) * 1e-6,                      # tiny positive (softmax-like)
+    ])
+    rows[1, ::97] = -0.0
+    got = ops.topk(rows.to(DEV), k, order=L.ORDER_VALUE_DESC).cpu()
+    assert torch.equal(got, O.stable_topk_desc(rows, k))
+    got = ops.topk(rows.to(DEV), k, order=L.ORDER_INDEX_ASC, tail=3).cpu()
+    exp = torch.cat([O.stable_topk_desc(rows, k).sort(-1).values, torch.arange(n, n + 3).expand(rows.shape[0], -1)], -1)
+    assert torch.equal(got, exp)
+
+
+def test_topk_head_sum_is_fixed_order():
+    from fastkv_b200 import ops
+    L = _lib()
+    x = torch.rand(3, 8, 5000, generator=torch.Generator().manual_seed(3))
+    idx, imp = ops.topk(x.to(DEV), 300, order=L.ORDER_INDEX_ASC, tail=8, nsum=8, return_importance=True)
+    ref = x[:, 0].clone()
+    for h in range(1, 8):
+        ref += x[:, h]
+    assert torch.equal(imp.cpu(), ref)
+    assert torch.equal(idx.cpu()[:, :300], O.stable_topk_desc(ref, 300).sort(-1).values)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_gather_rows_bit_exact(dtype):
+    from fastkv_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    hidden = torch.randn(2, 777, 4096, generator=g).to(dtype)
+    idx = torch.stack([torch.randperm(777, generator=g)[:100].sort().values for _ in range(2)])
+    pos = torch.arange(777).unsqueeze(0) + 5
+    nh, npos = ops.gather_rows(hidden.to(DEV), idx.to(DEV), pos.to(DEV))
+    eh, ep = O.tsp_propagate(hidden, pos.expand(2, -1), idx)
+    assert torch.equal(nh.cpu(), eh) and torch.equal(npos.cpu(), ep)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.bfloat16, 2e-2), (torch.float16, 2e-3), (torch.float32, 1e-5)])
+@pytest.mark.parametrize("b,hq,hkv,d,s,smax", [(1, 32, 8, 128, 2048, 2304), (8, 32, 8, 128, 520, 768), (2, 8, 8, 64, 77, 128),
+                                               (1, 16, 2, 128, 1, 64)])
+def test_decode_attention_vs_oracle(dtype, tol, b, hq, hkv, d, s, smax):
+    from fastkv_b200 import ops
+    g = torch.Generator().manual_seed(s)
+    q = torch.randn(b, hq, d, generator=g).to(dtype)
+    kc = torch.randn(b, hkv, smax, d, generator=g).to(dtype)
+    vc = torch.randn(b, hkv, smax, d, generator=g).to(dtype)
+    ref = O.decode_attention(q, kc, vc, s)
+    out = ops.decode_attn(q.to(DEV), kc.to(DEV), vc.to(DEV), s)
+    assert torch.allclose(out.cpu().float(), ref, atol=tol, rtol=tol)
+    # device-resident length (CUDA-graph friendly) gives the same answer
+    sl = torch.tensor([s], dtype=torch.int32, device=DEV)
+    out2 = ops.decode_attn(q.to(DEV), kc.to(DEV), vc.to(DEV), 0, seq_len_dev=sl)
+    assert torch.equal(out, out2)
+
+
+def test_cache_append_and_decode_loop():
+    from fastkv_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    b, hkv, d, s0, smax = 2, 8, 128, 40, 64
+    kc = torch.zeros(b, hkv, smax, d, dtype=torch.bfloat16, device=DEV)
+    vc = torch.zeros_like(kc)
+    base_k = torch.randn(b, hkv, s0, d, generator=g).bfloat16()
+    kc[:, :, :s0] = base_k.to(DEV)
+    sl = torch.tensor([s0], dtype=torch.int32, device=DEV)
+    news = []
+    for _ in range(5):
+        kn = torch.randn(b, 1, hkv, d, generator=g).bfloat16().to(DEV).transpose(1, 2)      # [B,Hkv,1,D] strided view
+        vn = torch.randn(b, 1, hkv, d, generator=g).bfloat16().to(DEV).transpose(1, 2)
+        ops.cache_append(kn, vn, kc, vc, 0, seq_len_dev=sl, bump=True)
+        news.append((kn, vn))
+    assert sl.item() == s0 + 5
+    for i, (kn, vn) in enumerate(news):
+        assert torch.equal(kc[:, :, s0 + i], kn[:, :, 0]) and torch.equal(vc[:, :, s0 + i], vn[:, :, 0])
+    assert torch.equal(kc[:, :, :s0].cpu(), base_k)
+
+
+def test_host_buffer_path_matches_device_path():
+    """update_kv on pinned host tensors (the e2e bench path) stages through the GPU kernels."""
+    from fastkv_b200 import FastKVCluster
+    knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)
+    q, k, v = make_inputs(21, 1, 32, 8, 2048, 128, layout="bhld")
+    a = FastKVCluster(**knobs).update_kv(k.pin_memory(), q.pin_memory(), v.pin_memory(), None, 4, 0)
+    b = FastKVCluster(**knobs).update_kv(k.to(DEV), q.to(DEV), v.to(DEV), None, 4, 0)
+    for x, y in zip(a, b):
+        assert not x.is_cuda and torch.equal(x, y.cpu())
+
+
+def test_bad_pooling_raises_like_the_reference():
+    from fastkv_b200 import FastKVCluster
+    q, k, v = [x.to(DEV) for x in make_inputs(1, 1, 8, 2, 256, 128)]
+    cl = FastKVCluster(window_size=8, max_capacity_prompt=64, pooling="minpool")
+    with pytest.raises(ValueError, match="Pooling method not supported"):
+        cl.update_kv(k, q, v, None, 4, 0)
