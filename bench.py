@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""Benchmark of the TSP + KV-compression hot path (BASELINE.json metric / configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--ctx 32768]
+
+One "step" = the hot path of ONE Llama-3.1-8B-shaped prefill: 32 ``update_kv`` calls
+(layers 0..tsp_idx at full context, the TSP layer additionally selecting tsp_len tokens and
+gathering the hidden states, the later layers at tsp_len tokens) on synthetic bf16 tensors.
+
+  value    algorithmic GB/s over the whole step with all inputs resident in HBM (CUDA-graph replay
+           of the C-ABI calls, per-layer distinct inputs so each step streams > L2 bytes)
+  e2e      same metric through the reference-facing ``FastKVCluster.update_kv`` with pinned HOST
+           buffers: host->device copies of K / V / Q-window and device->host reads of the results
+           inside the timed region
+  roofline the dominant kernel stage (observation-window scoring, K1+K2) timed alone with CUDA
+           events against MEASURED_PEAKS.json
+  cpu_baseline  the oracle port (torch CPU, same ATen ops as the reference) on this box's cores
+
+N > 1 (torchrun): weak scaling — N prompts, every rank owns Hkv/N KV heads of all of them, and
+the TSP layer does the path's one exchange (NCCL all-gather of the per-head scores) before the
+global top-k.  ``--impl reference`` times the oracle port only (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "tsp_kv_compress_algorithmic_hbm_throughput"
+UNIT = "GB/s"
+
+# Llama-3.1-8B-Instruct shape and BASELINE configs[1] knobs
+HQ, HKV, D, HIDDEN, LAYERS, TSP_IDX = 32, 8, 128, 4096, 32, 15
+W, KS, POOL = 8, 7, "avgpool"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ctx", type=int, default=32768)
+    ap.add_argument("--capacity", type=int, default=2048)
+    ap.add_argument("--tsp-len", type=int, default=2048)
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--score-impl", default="auto", choices=["auto", "simple", "tensor"])
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic bytes (stated in DESIGN.md)
+# ---------------------------------------------------------------------------------------------
+def layer_bytes(b, hkv, hq, l, c, tsp_t, e=2):
+    """Bytes one update_kv call must move: K read + Q-window read + score round trip + index write
+    + KV compaction (read + write of K and V rows); TSP layer adds the importance round trip,
+    the index set and the hidden-state gather."""
+    p = l - W
+    n = b * hkv * l * D * e                     # K read once
+    n += b * hq * W * D * e                     # Q window
+    n += 2 * b * hkv * p * 4                    # fp32 score written, read by top-k
+    n += b * hkv * (c - W) * 8                  # int64 indices
+    n += 2 * 2 * b * hkv * c * D * e            # K and V: C rows read + written
+    if tsp_t:
+        n += 2 * b * p * 4 + b * tsp_t * 8 + 2 * b * tsp_t * HIDDEN * e
+    return n
+
+
+def score_stage_bytes(b, hkv, hq, l, e=2):
+    return b * hkv * l * D * e + b * hq * W * D * e + b * hkv * (l - W) * 4
+
+
+def step_plan(ctx, cap, tsp_len):
+    """[(L, is_tsp_layer)] for the 32 layers of one prefill."""
+    plan = []
+    for i in range(LAYERS):
+        if i < TSP_IDX:
+            plan.append((ctx, False))
+        elif i == TSP_IDX:
+            plan.append((ctx, True))
+        else:
+            plan.append((tsp_len if ctx > tsp_len else ctx, False))
+    return plan
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampling
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step_sample(ctx, cap, tsp_len, reps):
+    """Times a bounded sample of the step on the CPU with the oracle port (same ATen op sequence as
+    baselines/fastkv/utils.py:80-134, fp32): one ordinary full-context layer, the TSP layer with the
+    hidden-state gather, and one post-TSP layer.  Returns (GB/s, seconds per sample, description)."""
+    from oracle import fastkv_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    g = torch.Generator().manual_seed(42)
+    q = torch.randn(1, HQ, ctx, D, generator=g)
+    k = torch.randn(1, HKV, ctx, D, generator=g)
+    v = torch.randn(1, HKV, ctx, D, generator=g)
+    hidden = torch.randn(1, ctx, HIDDEN, generator=g)
+    pos = torch.arange(ctx).unsqueeze(0)
+    short = min(tsp_len, ctx)
+    qs, ks_, vs = q[:, :, :short].contiguous(), k[:, :, :short].contiguous(), v[:, :, :short].contiguous()
+    knobs = dict(window_size=W, max_capacity_prompt=cap, kernel_size=KS, pooling=POOL, tsp_length=tsp_len)
+
+    def sample():
+        O.fastkv_update_kv(k, q, v, HQ // HKV, tsp_layer=False, **knobs)
+        tr = O.fastkv_update_kv(k, q, v, HQ // HKV, tsp_layer=True, **knobs)
+        if tr.tsp_idx is not None:
+            O.tsp_propagate(hidden, pos, tr.tsp_idx)
+        O.fastkv_update_kv(ks_, qs, vs, HQ // HKV, tsp_layer=False, **knobs)
+
+    nbytes = (layer_bytes(1, HKV, HQ, ctx, cap, 0) + layer_bytes(1, HKV, HQ, ctx, cap, tsp_len if ctx > tsp_len else 0)
+              + layer_bytes(1, HKV, HQ, short, min(cap, short), 0))
+    sample()                                            # warm-up (allocator, thread pool)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        sample()
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    desc = (f"3 of the 32 layer calls (1 full-context layer, the TSP layer + hidden gather, 1 post-TSP layer) at "
+            f"ctx={ctx}, fp32, median of {reps}")
+    return nbytes / med / 1e9, med, desc, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port, kind='port') on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    reps = max(1, args.steps)
+    for _ in range(max(0, args.warmup - 1)):
+        pass                                            # cpu_step_sample does its own warm-up call
+    gbs, sec, desc, cores = cpu_step_sample(args.ctx, args.capacity, args.tsp_len, reps)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": round(gbs, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, n):
+    return {
+        "workload": (f"BASELINE configs[1]: Llama-3.1-8B-shaped layer tensors (32 q / 8 kv heads, d=128, hidden 4096), "
+                     f"{args.ctx}-token prefill bf16, TSP at layer {TSP_IDX} with tsp_len={args.tsp_len}, KV budget "
+                     f"{args.capacity}, window {W}, kernel {KS} {POOL}; step = the 32 update_kv calls of one prefill "
+                     f"(+ hidden-state gather at the TSP layer)"),
+        "ctx": args.ctx, "capacity": args.capacity, "tsp_len": args.tsp_len, "window": W, "kernel_size": KS,
+        "pooling": POOL, "prompts": n, "sharding": f"kv-heads/{n}" if n > 1 else "none",
+        "l2": "per-layer distinct K/V/Q buffers: each step streams > 2 GB, far above the 126 MB L2",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from fastkv_b200 import FastKVCluster, ops, _lib as L
+    from fastkv_b200.dist import HeadShard
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    impl = {"auto": L.IMPL_AUTO, "simple": L.IMPL_SIMPLE, "tensor": L.IMPL_TENSOR}[args.score_impl]
+
+    n_prompts = world                                   # weak scaling: one prompt per GPU in the batch
+    hkv_local, hq_local = HKV // world, HQ // world
+    ctx, cap, tsp_len = args.ctx, args.capacity, args.tsp_len
+    plan = step_plan(ctx, cap, tsp_len)
+    shard = HeadShard(exchange="gather") if world > 1 else None
+
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+
+    def rand(b, l, h):
+        return torch.randn(b, l, h, D, generator=gen, device=dev, dtype=torch.bfloat16).transpose(1, 2)
+
+    layers = []
+    for (l, is_tsp) in plan:
+        q, k, v = rand(n_prompts, l, hq_local), rand(n_prompts, l, hkv_local), rand(n_prompts, l, hkv_local)
+        cl = FastKVCluster(window_size=W, max_capacity_prompt=cap, kernel_size=KS, pooling=POOL, tsp_layer=is_tsp,
+                           tsp_length=tsp_len)
+        cl.score_impl = impl
+        cl.shard = shard
+        layers.append((cl, q, k, v))
+    hidden = torch.randn(n_prompts, ctx, HIDDEN, generator=gen, device=dev, dtype=torch.bfloat16)
+    pos = torch.arange(ctx, device=dev).unsqueeze(0)
+
+    def one_step():
+        out = None
+        for (cl, q, k, v) in layers:
+            ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
+            if tsp is not None:
+                out = ops.gather_rows(hidden, tsp, pos)
+        return out
+
+    bytes_step = 0
+    for (l, is_tsp) in plan:
+        c_eff = cap
+        bytes_step += layer_bytes(n_prompts, hkv_local, hq_local, l, c_eff, tsp_len if (is_tsp and l > tsp_len) else 0)
+    total_bytes_step = bytes_step * world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, graph replay of the whole step --------------------------
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    c0 = lib.fkv_launch_count()
+    one_step()
+    launches_per_step = lib.fkv_launch_count() - c0
+    use_graph = (not args.no_graph) and world == 1
+    graph = None
+    if use_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                one_step()
+            graph.replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    run = graph.replay if graph is not None else one_step
+
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        run()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    value = total_bytes_step / (ms_step * 1e-3) / 1e9
+
+    # ---- roofline: scoring stage (K1+K2) timed alone, full-context layers, rotating inputs -------
+    full_layers = [(cl, q, k, v) for (cl, q, k, v), (l, _) in zip(layers, plan) if l == ctx]
+    reps = 0
+    for (cl, q, k, v) in full_layers[:3]:
+        ops.score(q, k, window_size=W, kernel_size=KS, pooling=POOL, impl=impl)
+    torch.cuda.synchronize()
+    c0 = lib.fkv_launch_count()
+    ops.score(full_layers[0][1], full_layers[0][2], window_size=W, kernel_size=KS, pooling=POOL, impl=impl)
+    score_kernels = lib.fkv_launch_count() - c0
+    torch.cuda.synchronize()
+    sev0, sev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sev0.record()
+    for _ in range(max(2, args.steps // 4)):
+        for (cl, q, k, v) in full_layers:
+            ops.score(q, k, window_size=W, kernel_size=KS, pooling=POOL, impl=impl)
+            reps += 1
+    sev1.record()
+    torch.cuda.synchronize()
+    score_us = sev0.elapsed_time(sev1) * 1e3 / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+    sbytes = score_stage_bytes(n_prompts, hkv_local, hq_local, ctx)
+    achieved = sbytes / (score_us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "score_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(str(ctx))
+        except Exception:  # noqa: BLE001
+            traffic = None
+    pp = L.ScoreParams()
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "fkv_score stage (K1+K2)",
+                "kernels_per_call": int(score_kernels), "us_per_call": round(score_us, 2),
+                "algorithmic_bytes_per_call": sbytes, "peak_source": peak_src}
+
+    # ---- e2e: FastKVCluster.update_kv on pinned HOST buffers -----------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_layers = []
+        q_host = {}
+        for (cl, q, k, v), (l, is_tsp) in zip(layers, plan):
+            if l not in q_host:                         # only the window rows of Q are ever read
+                q_host[l] = q.contiguous().cpu().pin_memory()
+            host_layers.append((cl, q_host[l], k.contiguous().cpu().pin_memory(), v.contiguous().cpu().pin_memory()))
+        hidden_host = hidden.cpu().pin_memory()
+        h2d = d2h = 0
+        es = 2
+        for (l, is_tsp) in plan:
+            h2d += n_prompts * (2 * hkv_local * l * D + hq_local * W * D) * es
+            d2h += 2 * n_prompts * hkv_local * min(cap, l) * D * es
+            if is_tsp and l > tsp_len:
+                h2d += n_prompts * ctx * HIDDEN * es
+                d2h += n_prompts * tsp_len * (8 + HIDDEN * es)
+
+        def host_step():
+            res = None
+            for (cl, q, k, v) in host_layers:
+                ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
+                if tsp is not None:
+                    res = ops.gather_rows(hidden_host.to(dev, non_blocking=True), tsp.to(dev), pos).cpu()
+            return res
+
+        for _ in range(2):
+            host_step()
+        e_steps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            host_step()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e_val = total_bytes_step / (dt.item() / e_steps) / 1e9
+        e2e = {"value": round(e_val, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": round(dt.item() / e_steps * 1e3, 3), "steps": e_steps,
+               "api": "FastKVCluster.update_kv(key_states, query_states, value_states, ...) on pinned host tensors"}
+
+    # ---- cpu baseline (rank 0, N == 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gbs, sec, desc, cores = cpu_step_sample(ctx, cap, tsp_len, 5)
+        cpu = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+               "seconds_per_sample": round(sec, 4)}
+
+    if rank == 0:
+        sp = L.ScoreParams()
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(args, n_prompts),
+            "algorithmic_bytes_per_step": int(total_bytes_step),
+            "timed_with": "cuda-graph replay of the C-ABI launches" if graph is not None else "eager C-ABI launches",
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
+            "launches_per_step": int(launches_per_step),
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,7 +111,7 @@ class CompressParams(C.Structure):
 
 EXPORTS = [
     "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
-    "fkv_score_impl_name",
+    "fkv_score_impl_name", "fkv_launch_count",
     "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append", "fkv_compress",
 ]
 
@@ -142,6 +142,7 @@ def load():
         lib.fkv_topk_workspace_bytes.argtypes = [C.c_int32] * 3
         lib.fkv_decode_workspace_bytes.restype = C.c_size_t
         lib.fkv_decode_workspace_bytes.argtypes = [C.c_int32] * 4
+        lib.fkv_launch_count.restype = C.c_uint64
         lib.fkv_score_impl_name.restype = C.c_char_p
         lib.fkv_score_impl_name.argtypes = [C.POINTER(ScoreParams)]
         for name, st in [("fkv_score", ScoreParams), ("fkv_topk", TopkParams), ("fkv_gather_kv", GatherKvParams),

@@ -7,6 +7,9 @@
 
 namespace fkv {
 
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
 int num_sms() {
   static std::atomic<int> cached{0};
   int v = cached.load(std::memory_order_relaxed);
@@ -82,6 +85,8 @@ using namespace fkv;
 extern "C" {
 
 int fkv_abi_version(void) { return FKV_ABI_VERSION; }
+
+uint64_t fkv_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* fkv_strerror(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);

@@ -22,6 +22,7 @@
   do {                                          \
     cudaError_t _e = cudaGetLastError();        \
     if (_e != cudaSuccess) return (int)_e;      \
+    ::fkv::count_launch();                      \
   } while (0)
 
 namespace fkv {
@@ -32,6 +33,7 @@ __host__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a
 
 inline int dtype_size(int dtype) { return dtype == FKV_F32 ? 4 : 2; }
 
+void count_launch();   // bumps the process-wide kernel-launch counter (abi.cu)
 int num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (abi.cu)
 
 // ---- element loads -> fp32 -----------------------------------------------------------------

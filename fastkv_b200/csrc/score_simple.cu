@@ -256,9 +256,14 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
   const int n_tiles = ceil_div(p.L, kTileKeys);
   a.n_tiles = n_tiles;
   const size_t smem = (size_t)(kTileKeys * (p.D + 4) + kRowChunk * p.D + kRowChunk * (kTileKeys + 1)) * sizeof(float);
-  FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kVotes>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;                      // once per process (and never inside a graph capture)
+  if (!attr_set) {
+    const int smem_max = (int)((kTileKeys * (128 + 4) + kRowChunk * 128 + kRowChunk * (kTileKeys + 1)) * sizeof(float));
+    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kVotes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    attr_set = true;
+  }
   char* ws = reinterpret_cast<char*>(p.workspace);
 
   if (p.mode == FKV_MODE_GEMFILTER) {

@@ -256,7 +256,12 @@ int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
       a.sort_ws = reinterpret_cast<unsigned long long*>(ws + off);
     }
   }
-  FKV_CUDA_TRY(cudaFuncSetAttribute(topk_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int smem_max = (int)((kMaxBins + kWarps + 4) * sizeof(uint32_t) + (size_t)kSmemSortMax * sizeof(unsigned long long));
+    FKV_CUDA_TRY(cudaFuncSetAttribute(topk_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    attr_set = true;
+  }
   topk_row_kernel<<<p.rows, kThreads, smem, s>>>(a);
   FKV_LAUNCH_CHECK();
   return FKV_OK;

@@ -215,6 +215,8 @@ size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k);
 size_t fkv_decode_workspace_bytes(int32_t B, int32_t Hq, int32_t D, int32_t max_seq_len);
 const char* fkv_strerror(int code);
 int fkv_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+uint64_t fkv_launch_count(void);
 /* Name of the scoring kernel that FKV_IMPL_AUTO picks for these parameters ("simple"/"tensor"). */
 const char* fkv_score_impl_name(const fkv_score_params* p);
 
