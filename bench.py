@@ -353,7 +353,6 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(str(ctx))
         except Exception:  # noqa: BLE001
             traffic = None
-    pp = L.ScoreParams()
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": traffic, "kernel": "fkv_score stage (K1+K2)",
                 "kernels_per_call": int(score_kernels), "us_per_call": round(score_us, 2),
@@ -383,7 +382,8 @@ def run_ours(args):
             for (cl, q, k, v) in host_layers:
                 ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
                 if tsp is not None:
-                    res = ops.gather_rows(hidden_host.to(dev, non_blocking=True), tsp.to(dev), pos).cpu()
+                    nh, npos = ops.gather_rows(hidden_host.to(dev, non_blocking=True), tsp.to(dev), pos)
+                    res = (nh.cpu(), npos.cpu())
             return res
 
         for _ in range(2):
@@ -410,7 +410,6 @@ def run_ours(args):
                "seconds_per_sample": round(sec, 4)}
 
     if rank == 0:
-        sp = L.ScoreParams()
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,

@@ -1,8 +1,608 @@
-// K1/K2 tensor-core path (tcgen05 + TMA).  Placeholder until the kernel lands: AUTO falls back
-// to the simple path, FKV_IMPL_TENSOR reports FKV_EMODE.
+// K1/K2 tensor-core path: fused observation-window scoring + pooling + GQA group-sum for 16-bit
+// inputs, hand-written for sm_100a (TMA -> shared memory -> tcgen05.mma -> TMEM -> registers).
+// Replaces baselines/fastkv/utils.py:93-112 (and the SnapKV twin) with ONE persistent kernel.
+//
+// Work unit  = (batch b, kv head h, key tile t).  A tile is 128 consecutive key rows (UMMA M) that
+//              start `half = kernel_size/2` rows before the S = 128 - 2*half keys it OWNS, so the
+//              pooling halo is recomputed instead of exchanged between CTAs.
+// MMA        = logits[128 keys x N] = K_tile[128 x D] . Qwin[N x D]^T, N = G*W window-rows of the
+//              G query heads of that kv head, bf16/f16 operands, fp32 accumulators in TMEM.
+// Two passes over the CTA's contiguous unit range, separated by one grid-wide barrier:
+//   pass 1   per row (max, sum exp2) over the owned keys (lazy per-warp rescaling), flushed per
+//            (b, h) pair to global partials
+//   pass 2   (tiles in reverse order: the most recently streamed K is still in L2)
+//            p = exp2(x - max) / sum  ->  votes per query head  ->  pool1d over the halo'd tile
+//            -> group-sum  ->  score[b, h, j]
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator,
+// warps 2-5 / 6-9 = two epilogue warpgroups that alternate tiles (double-buffered accumulators).
+#include <cuda.h>
+
+#include <mutex>
+
 #include "common.cuh"
 
 namespace fkv {
-bool score_tensor_supported(const fkv_score_params&) { return false; }
-int launch_score_tensor(const fkv_score_params&, cudaStream_t) { return FKV_EMODE; }
+namespace {
+
+constexpr int kTile = 128;
+constexpr int kTcThreads = 320;
+constexpr int kEpiThreads = 256;
+constexpr int kMaxLocalPairs = 8;
+constexpr int kMaxStages = 6;
+constexpr float kLazyTau = 6.0f;          // log2 units of headroom before a running max is raised
+constexpr float kEmptyMax = -1.0e30f;     // "no key seen yet" (finite, so exp2(x - m) never sees inf - inf)
+
+struct TcArgs {
+  int B, L, P, D, nkv, kv0, n_tiles, S, half, ks, pooling, group_sum, is_f16;
+  int U, maxlp, nst;
+  int kpos_l, kpos_h, kpos_b, qpos_l, qpos_h, qpos_b;   // coordinate slots of the stride-sorted TMA dims
+  int q_heads_per_kv;                                   // model G (query head = kvh * G + g)
+  float c;                                              // softmax scale * log2(e)
+  float2* part;                                         // [grid][maxlp][N] pass-1 partial (max, sum)
+  unsigned int* sync_counter;                           // zeroed before launch
+  float* score; int64_t score_sb, score_sh; int out_h0;
+};
+
+// ---- raw PTX wrappers ----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tWAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra WAIT_DONE;\n\tbra WAIT_LOOP;\n\tWAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+__device__ __forceinline__ void tmem_load_row(uint32_t taddr, float* v) {
+  if constexpr (N == 8) tmem_ld8(taddr, v);
+  else if constexpr (N == 16) tmem_ld16(taddr, v);
+  else {
+#pragma unroll
+    for (int c = 0; c < N; c += 32) tmem_ld32(taddr + c, v + c);
+  }
+}
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: LBO(enc)=1, SBO = 1024 B, version 1.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// which CTA owns unit u under the balanced split u0(c) = floor(c * U / grid)
+__device__ __forceinline__ int cta_of_unit(long long u, int U, int grid) { return (int)(((u + 1) * grid - 1) / U); }
+__device__ __forceinline__ int unit_begin(int c, int U, int grid) { return (int)((long long)c * U / grid); }
+
+template <int W, int G>
+__global__ void __launch_bounds__(kTcThreads, 1)
+score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_q, const TcArgs a) {
+  constexpr int N = W * G;                          // logit rows per (b, kv head)
+  constexpr int NMMA = N < 16 ? 16 : N;             // UMMA N (multiple of 16 for M = 128)
+  constexpr int TMEM_COLS = (2 * NMMA) < 32 ? 32 : 2 * NMMA;
+  static_assert(N <= 64 && (N & 7) == 0, "unsupported window x group size");
+
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
+
+  const int tile_bytes = kTile * a.D * 2;
+  const int q_bytes = NMMA * a.D * 2;
+  // carve-up (all operand regions 1024-byte aligned for the 128B swizzle)
+  const uint32_t k_off = 0;
+  const uint32_t q_off = k_off + a.nst * tile_bytes;
+  const uint32_t misc_off = q_off + 2 * ((q_bytes + 1023) & ~1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);          // full[6] empty[6] tfull[2] tempty[2] qfull[2] qempty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  float* mref = reinterpret_cast<float*>(tmem_slot + 4);                // [8][N]
+  float2* stage = reinterpret_cast<float2*>(mref + 8 * N);              // [8][N]
+  float2* colstat = stage + 8 * N;                                      // [maxlp][N]
+  int* vis_limit = reinterpret_cast<int*>(colstat + kMaxLocalPairs * N);  // [N]
+  float* vbuf = reinterpret_cast<float*>(vis_limit + N);                // [2 wg][2 buf][G][128]
+
+  auto bar_full = [&](int s) { return smem_u32(bars + s); };
+  auto bar_empty = [&](int s) { return smem_u32(bars + 6 + s); };
+  auto bar_tfull = [&](int s) { return smem_u32(bars + 12 + s); };
+  auto bar_tempty = [&](int s) { return smem_u32(bars + 14 + s); };
+  auto bar_qfull = [&](int s) { return smem_u32(bars + 16 + s); };
+  auto bar_qempty = [&](int s) { return smem_u32(bars + 18 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grid = gridDim.x, cta = blockIdx.x;
+  const int u0 = unit_begin(cta, a.U, grid), u1 = unit_begin(cta + 1, a.U, grid);
+  const int T = u1 - u0;                              // tiles of this CTA (>= 1: grid <= U)
+  const int pair0 = u0 / a.n_tiles;
+  const int nlp = (u1 - 1) / a.n_tiles - pair0 + 1;   // local (b, h) pairs touched
+  const int njobs = 2 * T;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128);
+      mbar_init(bar_qfull(s), 1); mbar_init(bar_qempty(s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (threadIdx.x >= 64 && threadIdx.x - 64 < N) {
+    const int n = threadIdx.x - 64;
+    vis_limit[n] = a.P + (n % W);                     // row r of the window sees window keys <= r (utils.py:95-101)
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // job j -> (local tile, pass): pass 1 ascending, pass 2 descending
+  auto job_tile = [&](int j) { return j < T ? j : (2 * T - 1 - j); };
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int cur_pair = -1, qu = -1;
+      for (int j = 0; j < njobs; ++j) {
+        const int u = u0 + job_tile(j);
+        const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
+        const int b = pair / a.nkv, kvh = a.kv0 + pair % a.nkv;
+        if (pair != cur_pair) {                      // new (b, h): stage its N query rows (B operand)
+          cur_pair = pair; ++qu;
+          const int qb = qu & 1;
+          if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
+          mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
+          const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
+          for (int slab = 0; slab < a.D / 64; ++slab)
+            for (int g = 0; g < G; ++g) {
+              int crd[4]; crd[0] = slab * 64; crd[a.qpos_l] = a.P; crd[a.qpos_h] = kvh * a.q_heads_per_kv + g; crd[a.qpos_b] = b;
+              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), crd[0], crd[1], crd[2], crd[3]);
+            }
+        }
+        const int slot = j % a.nst, use = j / a.nst;
+        if (use >= 1) mbar_wait(bar_empty(slot), (use - 1) & 1);
+        mbar_expect_tx(bar_full(slot), tile_bytes);
+        const uint32_t kdst = base + k_off + slot * tile_bytes;
+        const int row0 = t * a.S - a.half;           // may be negative / run past L: TMA zero-fills
+        for (int slab = 0; slab < a.D / 64; ++slab) {
+          int crd[4]; crd[0] = slab * 64; crd[a.kpos_l] = row0; crd[a.kpos_h] = kvh; crd[a.kpos_b] = b;
+          tma_load_4d(kdst + slab * (kTile * 128), &tm_k, bar_full(slot), crd[0], crd[1], crd[2], crd[3]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | ((a.is_f16 ? 0u : 1u) << 7) | ((a.is_f16 ? 0u : 1u) << 10) |
+                             ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+      int cur_pair = -1, qu = -1;
+      for (int j = 0; j < njobs; ++j) {
+        const int u = u0 + job_tile(j);
+        const int pair = u / a.n_tiles;
+        if (pair != cur_pair) {
+          cur_pair = pair; ++qu;
+          mbar_wait(bar_qfull(qu & 1), (qu >> 1) & 1);
+        }
+        const int slot = j % a.nst, use = j / a.nst;
+        const int acc = j & 1, acc_use = j >> 1;
+        mbar_wait(bar_full(slot), use & 1);
+        if (acc_use >= 1) mbar_wait(bar_tempty(acc), (acc_use - 1) & 1);
+        tc_fence_after();
+        const uint32_t ka = base + k_off + slot * tile_bytes;
+        const uint32_t qa = base + q_off + (qu & 1) * ((q_bytes + 1023) & ~1023);
+        const uint32_t d_tmem = tmem_base + acc * NMMA;
+        const int ksteps = a.D / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t ad = umma_desc_sw128(ka + (k >> 2) * (kTile * 128) + (k & 3) * 32);
+          const uint64_t bd = umma_desc_sw128(qa + (k >> 2) * (NMMA * 128) + (k & 3) * 32);
+          umma_f16(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_empty(slot));                // smem slot reusable once these MMAs retire
+        umma_commit(bar_tfull(acc));                 // accumulator ready for the epilogue
+        const bool last_of_pair = (j + 1 == njobs) || ((u0 + job_tile(j + 1)) / a.n_tiles != pair);
+        if (last_of_pair) umma_commit(bar_qempty(qu & 1));
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int et = threadIdx.x - 64;                 // 0..255
+    const int ew = et >> 5;                          // epilogue warp 0..7
+    const int wg = ew >> 2;                          // warpgroup 0/1 <-> accumulator stage
+    const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;             // tile row == TMEM lane
+    float* my_mref = mref + ew * N;
+    float z[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) z[n] = 0.f;
+    for (int n = lane; n < N; n += 32) my_mref[n] = kEmptyMax;
+    __syncwarp();
+
+    int flushed = 0;                                 // local pairs already flushed by this warpgroup
+    auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
+      for (; flushed < lp_end; ++flushed) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+          const float zs = warp_sum(z[n]);
+          if (lane == 0) stage[ew * N + n] = make_float2(my_mref[n], zs);
+          z[n] = 0.f;
+        }
+        __syncwarp();
+        for (int n = lane; n < N; n += 32) my_mref[n] = kEmptyMax;
+        named_bar(2, kEpiThreads);
+        if (et < N) {
+          float M = kEmptyMax;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) M = fmaxf(M, stage[w8 * N + et].x);
+          float Z = 0.f;
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) {
+            const float2 v = stage[w8 * N + et];
+            Z += v.y * ex2(v.x - M);
+          }
+          a.part[((size_t)cta * a.maxlp + flushed) * N + et] = make_float2(M, Z);
+        }
+        named_bar(2, kEpiThreads);
+      }
+    };
+
+    int j = wg;
+    // ---------------- pass 1: per-row softmax statistics over owned keys ----------------------
+    for (; j < T; j += 2) {
+      const int u = u0 + j;
+      const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
+      flush_upto(pair - pair0);
+      mbar_wait(bar_tfull(wg), (j >> 1) & 1);
+      tc_fence_after();
+      float s[N];
+      tmem_load_row<N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * NMMA, s);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_tempty(wg));
+      const int key = t * a.S - a.half + row;
+      const bool own = (row >= a.half) && (row < a.half + a.S) && (key < a.L);
+      const bool has_window = (t * a.S - a.half + kTile > a.P);
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        float x = s[n] * a.c;
+        bool vis = own;
+        if (has_window) vis = vis && (key <= vis_limit[n]);
+        x = vis ? x : -INFINITY;
+        float mn = my_mref[n];
+        if (__any_sync(0xffffffffu, x > mn + kLazyTau)) {
+          const float nm = fmaxf(warp_max(x), mn);
+          z[n] *= ex2(mn - nm);
+          mn = nm;
+          __syncwarp();
+          if (lane == 0) my_mref[n] = nm;
+          __syncwarp();
+        }
+        z[n] += ex2(x - mn);
+      }
+    }
+    flush_upto(nlp);
+
+    // ---------------- grid barrier: every CTA's partials are visible ---------------------------
+    __threadfence();
+    named_bar(2, kEpiThreads);
+    if (et == 0) {
+      atomicAdd(a.sync_counter, 1u);
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sync_counter) : "memory");
+        if (seen < (unsigned)grid) __nanosleep(64);
+      } while (seen < (unsigned)grid);
+    }
+    named_bar(2, kEpiThreads);
+
+    // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
+    for (int idx = et; idx < nlp * N * 8; idx += kEpiThreads) {
+      const int sub = idx & 7, n = (idx >> 3) % N, lp = (idx >> 3) / N;
+      const int pair = pair0 + lp;
+      const long long ub = (long long)pair * a.n_tiles;
+      const long long ue = ub + a.n_tiles - 1;
+      const int c_lo = cta_of_unit(ub, a.U, grid), c_hi = cta_of_unit(ue, a.U, grid);
+      float M = kEmptyMax, Z = 0.f;
+      for (int c = c_lo + sub; c <= c_hi; c += 8) {
+        const int lpc = pair - unit_begin(c, a.U, grid) / a.n_tiles;
+        const float2 v = __ldcg(a.part + ((size_t)c * a.maxlp + lpc) * N + n);
+        const float nm = fmaxf(M, v.x);
+        Z = Z * ex2(M - nm) + v.y * ex2(v.x - nm);
+        M = nm;
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, M, o), oz = __shfl_xor_sync(0xffffffffu, Z, o);
+        const float nm = fmaxf(M, om);
+        Z = Z * ex2(M - nm) + oz * ex2(om - nm);
+        M = nm;
+      }
+      if (sub == 0) colstat[lp * N + n] = make_float2(M, 1.0f / Z);
+    }
+    named_bar(2, kEpiThreads);
+
+    // ---------------- pass 2: votes -> pool -> group sum -> score ------------------------------
+    // continue the same job sequence: this warpgroup owns jobs j = wg, wg+2, ...
+    // (j left the pass-1 loop as the first own job index >= T)
+    const float pad = (a.pooling == FKV_POOL_MAX) ? -INFINITY : 0.f;
+    for (; j < njobs; j += 2) {
+      const int u = u0 + (2 * T - 1 - j);
+      const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
+      const int lp = pair - pair0;
+      const int b = pair / a.nkv, kvl = pair % a.nkv;
+      mbar_wait(bar_tfull(wg), (j >> 1) & 1);
+      tc_fence_after();
+      float s[N];
+      tmem_load_row<N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * NMMA, s);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(bar_tempty(wg));
+      const int key = t * a.S - a.half + row;
+      const bool in_prefix = (key >= 0) && (key < a.P);
+      float* vb = vbuf + ((wg * 2 + ((j >> 1) & 1)) * G) * kTile;
+      const float2* cs = colstat + lp * N;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        float vote = 0.f;
+#pragma unroll
+        for (int r = 0; r < W; ++r) {
+          const float2 mz = cs[g * W + r];
+          vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mz.x)), mz.y, vote);   // rows summed in order (utils.py:104)
+        }
+        vb[g * kTile + row] = in_prefix ? vote : pad;
+      }
+      named_bar(3 + wg, 128);
+      const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
+      if (own) {
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          float pooled;
+          if (a.pooling == FKV_POOL_MAX) {
+            pooled = -INFINITY;
+            for (int d = -a.half; d <= a.half; ++d) pooled = fmaxf(pooled, vb[g * kTile + row + d]);
+          } else {
+            float sum = 0.f;
+            for (int d = -a.half; d <= a.half; ++d) sum += vb[g * kTile + row + d];
+            pooled = sum / (float)a.ks;               // count_include_pad: always / kernel_size
+          }
+          if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
+          else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * G + g - a.out_h0) * a.score_sh + key] = pooled;
+        }
+        if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  });
+  return fn;
+}
+
+// [B,H,L,D] view -> 4-D tensor map (dim0 = D, the other three sorted by stride) with a
+// (64 x box_rows x 1 x 1) box on (D, L); reports the coordinate slot of l / h / b.
+int make_map(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int L, int D, int box_rows, int* pos_l,
+             int* pos_h, int* pos_b) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return (int)cudaErrorNotSupported;
+  struct Dim { uint64_t size, stride; int box, id; } d[3] = {
+      {(uint64_t)L, (uint64_t)v.stride_l * 2, box_rows, 0},
+      {(uint64_t)H, (uint64_t)v.stride_h * 2, 1, 1},
+      {(uint64_t)B, (uint64_t)v.stride_b * 2, 1, 2}};
+  for (int i = 0; i < 3; ++i)
+    if (d[i].size == 1) d[i].stride = 0;             // degenerate dims get a harmless stride below
+  // sort by stride (degenerate dims last)
+  for (int i = 0; i < 3; ++i)
+    for (int j = i + 1; j < 3; ++j) {
+      const uint64_t si = d[i].size == 1 ? ~0ull : d[i].stride, sj = d[j].size == 1 ? ~0ull : d[j].stride;
+      if (sj < si) { Dim t = d[i]; d[i] = d[j]; d[j] = t; }
+    }
+  cuuint64_t gdim[4] = {(cuuint64_t)D, d[0].size, d[1].size, d[2].size};
+  cuuint64_t gstr[3];
+  uint64_t prev = (uint64_t)D * 2;
+  for (int i = 0; i < 3; ++i) {
+    uint64_t s = d[i].stride;
+    if (d[i].size == 1 || s == 0) s = prev * (i == 0 ? 1 : gdim[i]);   // any multiple of 16 works for a size-1 dim
+    gstr[i] = s;
+    prev = s;
+  }
+  cuuint32_t box[4] = {64, (cuuint32_t)d[0].box, (cuuint32_t)d[1].box, (cuuint32_t)d[2].box};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i) {
+    if (d[i].id == 0) *pos_l = i + 1;
+    if (d[i].id == 1) *pos_h = i + 1;
+    if (d[i].id == 2) *pos_b = i + 1;
+  }
+  const CUtensorMapDataType dt = dtype == FKV_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUresult r = fn(map, dt, 4, const_cast<void*>(v.ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? FKV_OK : (int)cudaErrorInvalidValue;
+}
+
+struct Plan {
+  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst;
+  size_t smem, part_bytes;
+  bool ok;
+};
+
+Plan make_plan(const fkv_score_params& p) {
+  Plan pl{};
+  pl.ok = false;
+  if (p.dtype != FKV_BF16 && p.dtype != FKV_F16) return pl;
+  if (p.mode != FKV_MODE_FASTKV && p.mode != FKV_MODE_SNAPKV) return pl;
+  const int Gm = p.Hq / p.Hkv;
+  pl.G = Gm; pl.W = p.window_size; pl.N = pl.G * pl.W;
+  if (!(pl.W == 8 || pl.W == 16 || pl.W == 32) || pl.N > 64) return pl;
+  if (p.mode == FKV_MODE_SNAPKV) {
+    if (p.h0 % Gm || p.h1 % Gm) return pl;           // whole kv-head groups only
+    pl.kv0 = p.h0 / Gm; pl.nkv = (p.h1 - p.h0) / Gm;
+  } else {
+    pl.kv0 = p.h0; pl.nkv = p.h1 - p.h0;
+  }
+  pl.half = p.kernel_size / 2;
+  pl.S = kTile - 2 * pl.half;
+  if (pl.S < 32) return pl;
+  pl.n_tiles = ceil_div(p.L, pl.S);
+  const long long U = (long long)p.B * pl.nkv * pl.n_tiles;
+  if (U > (1ll << 30)) return pl;
+  pl.U = (int)U;
+  pl.grid = (int)(U < num_sms() ? U : num_sms());
+  const int per = ceil_div(pl.U, pl.grid);
+  pl.maxlp = ceil_div(per, pl.n_tiles) + 1;
+  if (pl.maxlp > kMaxLocalPairs) return pl;
+  const int NMMA = pl.N < 16 ? 16 : pl.N;
+  const size_t tile_bytes = (size_t)kTile * p.D * 2;
+  const size_t q_bytes = ((size_t)NMMA * p.D * 2 + 1023) & ~(size_t)1023;
+  const size_t misc = 24 * 8 + 16 + (size_t)8 * pl.N * 4 + (size_t)8 * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 +
+                      (size_t)pl.N * 4 + (size_t)2 * 2 * pl.G * kTile * 4;
+  const size_t budget = 227 * 1024 - 1024 - 2 * q_bytes - misc - 256;
+  int nst = (int)(budget / tile_bytes);
+  if (nst > kMaxStages) nst = kMaxStages;
+  if (nst < 2) return pl;
+  pl.nst = nst;
+  pl.smem = 1024 + nst * tile_bytes + 2 * q_bytes + misc + 256;
+  pl.part_bytes = align_up((size_t)pl.grid * pl.maxlp * pl.N * sizeof(float2), 256);
+  pl.ok = true;
+  return pl;
+}
+
+template <int W, int G>
+int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, int grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tc_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kTcThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the in-kernel grid barrier is safe
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G>, mk, mq, a));
+  count_launch();
+  return FKV_OK;
+}
+
+}  // namespace
+
+bool score_tensor_supported(const fkv_score_params& p) { return make_plan(p).ok && encode_fn() != nullptr; }
+
+int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
+  const Plan pl = make_plan(p);
+  if (!pl.ok) return FKV_EMODE;
+  if (p.workspace_bytes < pl.part_bytes + 256) return FKV_EWORKSPACE;
+  TcArgs a{};
+  a.B = p.B; a.L = p.L; a.P = p.L - p.window_size; a.D = p.D;
+  a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
+  a.pooling = p.pooling; a.group_sum = (p.mode == FKV_MODE_FASTKV); a.is_f16 = (p.dtype == FKV_F16);
+  a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.q_heads_per_kv = pl.G;
+  a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
+  char* ws = reinterpret_cast<char*>(p.workspace);
+  a.sync_counter = reinterpret_cast<unsigned int*>(ws);
+  a.part = reinterpret_cast<float2*>(ws + 256);
+  a.score = p.score; a.score_sb = p.score_stride_b; a.score_sh = p.score_stride_h; a.out_h0 = p.h0;
+
+  CUtensorMap mk, mq;
+  int rc;
+  if ((rc = make_map(&mk, p.k, p.dtype, p.B, p.Hkv, p.L, p.D, kTile, &a.kpos_l, &a.kpos_h, &a.kpos_b)) != FKV_OK) return rc;
+  if ((rc = make_map(&mq, p.q, p.dtype, p.B, p.Hq, p.L, p.D, pl.W, &a.qpos_l, &a.qpos_h, &a.qpos_b)) != FKV_OK) return rc;
+  FKV_CUDA_TRY(cudaMemsetAsync(a.sync_counter, 0, 4, s));
+
+#define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) return launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
+  FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4); FKV_TC_CASE(8, 8);
+  FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2); FKV_TC_CASE(16, 4);
+  FKV_TC_CASE(32, 1); FKV_TC_CASE(32, 2);
+#undef FKV_TC_CASE
+  return FKV_EMODE;
+}
+
 }  // namespace fkv
