@@ -17,6 +17,8 @@
 // warps 2-5 / 6-9 = two epilogue warpgroups that alternate tiles (double-buffered accumulators).
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -40,6 +42,7 @@ struct TcArgs {
   float c;                                              // softmax scale * log2(e)
   float2* part;                                         // [grid][maxlp][N] pass-1 partial (max, sum)
   unsigned int* sync_counter;                           // zeroed before launch
+  unsigned long long* trace;                            // optional [grid][16] globaltimer stamps (FKV_TC_TRACE=1)
   float* score; int64_t score_sb, score_sh; int out_h0;
 };
 
@@ -122,6 +125,14 @@ __device__ __forceinline__ void tmem_load_row(uint32_t taddr, float* v) {
   }
 }
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define FKV_TRACE2(role, m) do { if (a.trace && blockIdx.x == 0 && (m) < 64) a.trace[256 * 16 + (role) * 64 + (m)] = gtimer(); } while (0)
+#define FKV_TRACE(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -142,10 +153,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_q, const TcArgs a) {
   constexpr int N = W * G;                          // logit rows per (b, kv head)
   constexpr int NMMA = N < 16 ? 16 : N;             // UMMA N (multiple of 16 for M = 128)
-  constexpr int TMEM_COLS = (2 * NMMA) < 32 ? 32 : 2 * NMMA;
+  constexpr int NB = 512 / NMMA;                    // accumulator blocks: ALL of TMEM is a logits cache
   static_assert(N <= 64 && (N & 7) == 0, "unsupported window x group size");
 
   extern __shared__ unsigned char smem_dyn[];
+  if (threadIdx.x == 64) FKV_TRACE(0);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
 
@@ -155,20 +167,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   const uint32_t k_off = 0;
   const uint32_t q_off = k_off + a.nst * tile_bytes;
   const uint32_t misc_off = q_off + 2 * ((q_bytes + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);          // full[6] empty[6] tfull[2] tempty[2] qfull[2] qempty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-  float* mref = reinterpret_cast<float*>(tmem_slot + 4);                // [8][N]
-  float2* stage = reinterpret_cast<float2*>(mref + 8 * N);              // [8][N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);   // full[6] empty[6] qfull[2] qempty[2] tfull[32] tempty[32] rdone[32]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 112);
+  float2* stage = reinterpret_cast<float2*>(tmem_slot + 4);             // [8][N]
   float2* colstat = stage + 8 * N;                                      // [maxlp][N]
-  int* vis_limit = reinterpret_cast<int*>(colstat + kMaxLocalPairs * N);  // [N]
-  float* vbuf = reinterpret_cast<float*>(vis_limit + N);                // [2 wg][2 buf][G][128]
+  float* vbuf = reinterpret_cast<float*>(colstat + kMaxLocalPairs * N); // [2 wg][2 buf][G][128]
 
   auto bar_full = [&](int s) { return smem_u32(bars + s); };
   auto bar_empty = [&](int s) { return smem_u32(bars + 6 + s); };
-  auto bar_tfull = [&](int s) { return smem_u32(bars + 12 + s); };
-  auto bar_tempty = [&](int s) { return smem_u32(bars + 14 + s); };
-  auto bar_qfull = [&](int s) { return smem_u32(bars + 16 + s); };
-  auto bar_qempty = [&](int s) { return smem_u32(bars + 18 + s); };
+  auto bar_qfull = [&](int s) { return smem_u32(bars + 12 + s); };
+  auto bar_qempty = [&](int s) { return smem_u32(bars + 14 + s); };
+  auto bar_tfull = [&](int s) { return smem_u32(bars + 16 + s); };
+  auto bar_tempty = [&](int s) { return smem_u32(bars + 48 + s); };
+  auto bar_rdone = [&](int s) { return smem_u32(bars + 80 + s); };   // resident tile re-read in pass 2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grid = gridDim.x, cta = blockIdx.x;
@@ -176,61 +187,84 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   const int T = u1 - u0;                              // tiles of this CTA (>= 1: grid <= U)
   const int pair0 = u0 / a.n_tiles;
   const int nlp = (u1 - 1) / a.n_tiles - pair0 + 1;   // local (b, h) pairs touched
-  const int njobs = 2 * T;
+  // MMA jobs: pass 1 computes every tile (ascending) into TMEM block tile % NB; the last
+  // min(T, NB) tiles therefore stay resident and pass 2 only recomputes tiles T-NB-1 .. 0.
+  const int n_refill = T > NB ? T - NB : 0;
+  const int n_mma_jobs = T + n_refill;
+  auto mma_job_tile = [&](int m) { return m < T ? m : (T - NB - 1 - (m - T)); };
+  // fills of block b during pass 1
+  auto fills_pass1 = [&](int b) { return (T - 1 - b) / NB + 1; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128);
-      mbar_init(bar_qfull(s), 1); mbar_init(bar_qempty(s), 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(bar_qfull(s), 1); mbar_init(bar_qempty(s), 1); }
+    for (int s = 0; s < NB; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128); mbar_init(bar_rdone(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  if (threadIdx.x >= 64 && threadIdx.x - 64 < N) {
-    const int n = threadIdx.x - 64;
-    vis_limit[n] = a.P + (n % W);                     // row r of the window sees window keys <= r (utils.py:95-101)
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q) : "memory");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // job j -> (local tile, pass): pass 1 ascending, pass 2 descending
-  auto job_tile = [&](int j) { return j < T ? j : (2 * T - 1 - j); };
+  if (threadIdx.x == 64) FKV_TRACE(1);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
+    // One thread; everything in the loop is incremental (no divisions, no local arrays): at
+    // ~5 cycles per dependent instruction a fat loop body would pace the whole pipeline.
     if (lane == 0) {
+      // coordinate slot k of the stride-sorted tensor map receives row / head / batch
+      const int kl1 = a.kpos_l == 1, kl2 = a.kpos_l == 2, kl3 = a.kpos_l == 3;
+      const int kh1 = a.kpos_h == 1, kh2 = a.kpos_h == 2, kh3 = a.kpos_h == 3;
+      const int kb1 = a.kpos_b == 1, kb2 = a.kpos_b == 2, kb3 = a.kpos_b == 3;
+      const int ql1 = a.qpos_l == 1, ql2 = a.qpos_l == 2, ql3 = a.qpos_l == 3;
+      const int qh1 = a.qpos_h == 1, qh2 = a.qpos_h == 2, qh3 = a.qpos_h == 3;
+      const int qb1 = a.qpos_b == 1, qb2 = a.qpos_b == 2, qb3 = a.qpos_b == 3;
+      const int slabs = a.D >> 6;
       int cur_pair = -1, qu = -1;
-      for (int j = 0; j < njobs; ++j) {
-        const int u = u0 + job_tile(j);
-        const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
-        const int b = pair / a.nkv, kvh = a.kv0 + pair % a.nkv;
+      int pair = pair0, t = u0 - pair0 * a.n_tiles;  // cursor of the next tile to load
+      int hb1 = 0, hb2 = 0, hb3 = 0;                 // head/batch part of the K coordinates
+      int slot = 0, ephase = 1;                      // ring slot + parity for the empty-barrier wait
+      for (int m = 0; m < n_mma_jobs; ++m) {
+        if (m == T) {                                // pass-2 refills restart at tile T-NB-1, descending
+          const int u = u0 + T - NB - 1;
+          pair = u / a.n_tiles; t = u - pair * a.n_tiles;
+        }
         if (pair != cur_pair) {                      // new (b, h): stage its N query rows (B operand)
           cur_pair = pair; ++qu;
+          const int b = pair / a.nkv, kvh = a.kv0 + pair - b * a.nkv;
+          hb1 = kvh * kh1 + b * kb1; hb2 = kvh * kh2 + b * kb2; hb3 = kvh * kh3 + b * kb3;
           const int qb = qu & 1;
           if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
           mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
           const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
-          for (int slab = 0; slab < a.D / 64; ++slab)
+          for (int slab = 0; slab < slabs; ++slab)
+#pragma unroll
             for (int g = 0; g < G; ++g) {
-              int crd[4]; crd[0] = slab * 64; crd[a.qpos_l] = a.P; crd[a.qpos_h] = kvh * a.q_heads_per_kv + g; crd[a.qpos_b] = b;
-              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), crd[0], crd[1], crd[2], crd[3]);
+              const int hq = kvh * a.q_heads_per_kv + g;
+              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
+                          a.P * ql1 + hq * qh1 + b * qb1, a.P * ql2 + hq * qh2 + b * qb2, a.P * ql3 + hq * qh3 + b * qb3);
             }
         }
-        const int slot = j % a.nst, use = j / a.nst;
-        if (use >= 1) mbar_wait(bar_empty(slot), (use - 1) & 1);
+        if (m >= a.nst) mbar_wait(bar_empty(slot), ephase);
+        FKV_TRACE2(0, m);
         mbar_expect_tx(bar_full(slot), tile_bytes);
         const uint32_t kdst = base + k_off + slot * tile_bytes;
         const int row0 = t * a.S - a.half;           // may be negative / run past L: TMA zero-fills
-        for (int slab = 0; slab < a.D / 64; ++slab) {
-          int crd[4]; crd[0] = slab * 64; crd[a.kpos_l] = row0; crd[a.kpos_h] = kvh; crd[a.kpos_b] = b;
-          tma_load_4d(kdst + slab * (kTile * 128), &tm_k, bar_full(slot), crd[0], crd[1], crd[2], crd[3]);
-        }
+        const int c1 = row0 * kl1 + hb1, c2 = row0 * kl2 + hb2, c3 = row0 * kl3 + hb3;
+        tma_load_4d(kdst, &tm_k, bar_full(slot), 0, c1, c2, c3);
+        if (slabs == 2) tma_load_4d(kdst + kTile * 128, &tm_k, bar_full(slot), 64, c1, c2, c3);
+        if (m == T - 1) FKV_TRACE(10);
+        if (++slot == a.nst) { slot = 0; ephase ^= 1; }
+        if (m < T) { if (++t == a.n_tiles) { t = 0; ++pair; } }
+        else       { if (--t < 0) { t = a.n_tiles - 1; --pair; } }
       }
     }
   } else if (warp == 1) {
@@ -238,60 +272,104 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | ((a.is_f16 ? 0u : 1u) << 7) | ((a.is_f16 ? 0u : 1u) << 10) |
                              ((uint32_t)(NMMA >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const bool two_slabs = (a.D == 128);
       int cur_pair = -1, qu = -1;
-      for (int j = 0; j < njobs; ++j) {
-        const int u = u0 + job_tile(j);
-        const int pair = u / a.n_tiles;
+      int pair = pair0, t = u0 - pair0 * a.n_tiles;
+      int lt = 0;
+      int slot = 0, fphase = 0;
+      uint32_t qa = 0;
+      for (int m = 0; m < n_mma_jobs; ++m) {
+        if (m == T) {
+          lt = T - NB - 1;
+          const int u = u0 + lt;
+          pair = u / a.n_tiles; t = u - pair * a.n_tiles;
+        }
         if (pair != cur_pair) {
           cur_pair = pair; ++qu;
           mbar_wait(bar_qfull(qu & 1), (qu >> 1) & 1);
+          qa = base + q_off + (qu & 1) * ((q_bytes + 1023) & ~1023);
         }
-        const int slot = j % a.nst, use = j / a.nst;
-        const int acc = j & 1, acc_use = j >> 1;
-        mbar_wait(bar_full(slot), use & 1);
-        if (acc_use >= 1) mbar_wait(bar_tempty(acc), (acc_use - 1) & 1);
+        const int blk = lt & (NB - 1);
+        mbar_wait(bar_full(slot), fphase);
+        FKV_TRACE2(1, m);
+        // The block must have been drained by the epilogue.  tempty[blk] completes one phase per
+        // consumed FILL, so "fill f may start" == "phase f-1 complete" and the waiter is never more
+        // than one phase behind (parity waits cannot express a longer lag).  The pass-2 re-read of
+        // the tile left resident by pass 1 is tracked by its own single-phase barrier rdone[blk].
+        {
+          int fill;
+          if (m < T) fill = lt / NB;
+          else {
+            const int n1 = fills_pass1(blk);
+            fill = 2 * n1 - 2 - lt / NB;                           // n1 + (n1 - 2 - lt/NB)
+            if (fill == n1) mbar_wait(bar_rdone(blk), 0);
+          }
+          if (fill >= 1) mbar_wait(bar_tempty(blk), (fill - 1) & 1);
+        }
         tc_fence_after();
         const uint32_t ka = base + k_off + slot * tile_bytes;
-        const uint32_t qa = base + q_off + (qu & 1) * ((q_bytes + 1023) & ~1023);
-        const uint32_t d_tmem = tmem_base + acc * NMMA;
-        const int ksteps = a.D / 16;
-        for (int k = 0; k < ksteps; ++k) {
-          const uint64_t ad = umma_desc_sw128(ka + (k >> 2) * (kTile * 128) + (k & 3) * 32);
-          const uint64_t bd = umma_desc_sw128(qa + (k >> 2) * (NMMA * 128) + (k & 3) * 32);
-          umma_f16(d_tmem, ad, bd, idesc, k > 0 ? 1u : 0u);
+        const uint32_t d_tmem = tmem_base + blk * NMMA;
+        const uint64_t ad0 = desc_hi | (uint64_t)((ka & 0x3ffffu) >> 4);
+        const uint64_t bd0 = desc_hi | (uint64_t)((qa & 0x3ffffu) >> 4);
+        // K advances 16 elements = 32 B (encoded +2) inside the 128B swizzle atom; the second
+        // 64-wide slab of D starts one full operand slab later
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+        if (two_slabs) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, ad0 + ((kTile * 128) >> 4) + 2 * k, bd0 + ((NMMA * 128) >> 4) + 2 * k, idesc, 1u);
         }
         umma_commit(bar_empty(slot));                // smem slot reusable once these MMAs retire
-        umma_commit(bar_tfull(acc));                 // accumulator ready for the epilogue
-        const bool last_of_pair = (j + 1 == njobs) || ((u0 + job_tile(j + 1)) / a.n_tiles != pair);
-        if (last_of_pair) umma_commit(bar_qempty(qu & 1));
+        umma_commit(bar_tfull(blk));                 // accumulator ready for the epilogue
+        if (m == T - 1) FKV_TRACE(9);
+        FKV_TRACE2(2, m);
+        if (++slot == a.nst) { slot = 0; fphase ^= 1; }
+        // advance the cursor; release the Q buffer after the last tile of a pair
+        int npair = pair;
+        if (m < T) { ++lt; if (++t == a.n_tiles) { t = 0; ++npair; } }
+        else       { --lt; if (--t < 0) { t = a.n_tiles - 1; --npair; } }
+        if (m == T - 1 && n_refill > 0) npair = (u0 + T - NB - 1) / a.n_tiles;   // the cursor jumps there next
+        if (m + 1 == n_mma_jobs || npair != pair) umma_commit(bar_qempty(qu & 1));
+        pair = npair;
       }
     }
   } else {
     // ===================================== epilogue =========================================
     const int et = threadIdx.x - 64;                 // 0..255
     const int ew = et >> 5;                          // epilogue warp 0..7
-    const int wg = ew >> 2;                          // warpgroup 0/1 <-> accumulator stage
+    const int wg = ew >> 2;                          // warpgroup 0/1: alternate tiles
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;             // tile row == TMEM lane
-    float* my_mref = mref + ew * N;
-    float z[N];
+    const uint32_t my_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    // Per-warp running reference max (warp-uniform, replicated in every lane) and per-lane partial
+    // sums, both in registers.  In pass 2 the same registers hold the final (max, 1/sum) per row.
+    float mn[N], z[N];
 #pragma unroll
-    for (int n = 0; n < N; ++n) z[n] = 0.f;
-    for (int n = lane; n < N; n += 32) my_mref[n] = kEmptyMax;
-    __syncwarp();
+    for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
 
     int flushed = 0;                                 // local pairs already flushed by this warpgroup
     auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
       for (; flushed < lp_end; ++flushed) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) {
-          const float zs = warp_sum(z[n]);
-          if (lane == 0) stage[ew * N + n] = make_float2(my_mref[n], zs);
-          z[n] = 0.f;
+        for (int n0 = 0; n0 < N; n0 += 8) {          // 8 independent shuffle chains at a time
+          float t8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) t8[i] = z[n0 + i];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t8[i] += __shfl_xor_sync(0xffffffffu, t8[i], o);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (lane == i) stage[ew * N + n0 + i] = make_float2(mn[n0 + i], t8[i]);
         }
-        __syncwarp();
-        for (int n = lane; n < N; n += 32) my_mref[n] = kEmptyMax;
+#pragma unroll
+        for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+        if (et == 0) FKV_TRACE(11);
         named_bar(2, kEpiThreads);
+        if (et == 0) FKV_TRACE(12);
         if (et < N) {
           float M = kEmptyMax;
 #pragma unroll
@@ -308,56 +386,83 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       }
     };
 
-    int j = wg;
     // ---------------- pass 1: per-row softmax statistics over owned keys ----------------------
-    for (; j < T; j += 2) {
-      const int u = u0 + j;
-      const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
+    int pair, t;
+    { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
+    for (int j = wg; j < T; j += 2) {
+      const int blk = j & (NB - 1);
       flush_upto(pair - pair0);
-      mbar_wait(bar_tfull(wg), (j >> 1) & 1);
+      mbar_wait(bar_tfull(blk), (j / NB) & 1);
+      if (et == 0 && j == 0) FKV_TRACE(2);
+      if ((et & 127) == 0) FKV_TRACE2(3, j);
       tc_fence_after();
       float s[N];
-      tmem_load_row<N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * NMMA, s);
+      tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(bar_tempty(wg));
+      mbar_arrive(bar_tempty(blk));
       const int key = t * a.S - a.half + row;
       const bool own = (row >= a.half) && (row < a.half + a.S) && (key < a.L);
-      const bool has_window = (t * a.S - a.half + kTile > a.P);
+      const bool has_window = (t * a.S - a.half + kTile > a.P);   // warp-uniform
+      const int kp = key - a.P;                      // window key index (>= 0 inside the window)
+      // window row r sees window keys <= r (utils.py:95-101): mask the others to -inf
+      if (has_window) {
 #pragma unroll
-      for (int n = 0; n < N; ++n) {
-        float x = s[n] * a.c;
-        bool vis = own;
-        if (has_window) vis = vis && (key <= vis_limit[n]);
-        x = vis ? x : -INFINITY;
-        float mn = my_mref[n];
-        if (__any_sync(0xffffffffu, x > mn + kLazyTau)) {
-          const float nm = fmaxf(warp_max(x), mn);
-          z[n] *= ex2(mn - nm);
-          mn = nm;
-          __syncwarp();
-          if (lane == 0) my_mref[n] = nm;
-          __syncwarp();
-        }
-        z[n] += ex2(x - mn);
+        for (int n = 0; n < N; ++n) s[n] = (kp > (n % W)) ? -INFINITY : s[n];
       }
+      // cheap check first: does any owned key exceed its row's reference by more than tau?
+      float dmax = -INFINITY;
+#pragma unroll
+      for (int n = 0; n < N; ++n) dmax = fmaxf(dmax, fmaf(s[n], a.c, -mn[n]));
+      if (__any_sync(0xffffffffu, own && dmax > kLazyTau)) {
+        // rare (always on the first tile of a pair): raise the references, 8 rows per round
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 8) {
+          float cm[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cm[i] = own ? s[n0 + i] * a.c : -INFINITY;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cm[i] = fmaxf(cm[i], __shfl_xor_sync(0xffffffffu, cm[i], o));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float nm = fmaxf(mn[n0 + i], cm[i]);
+            z[n0 + i] *= ex2(mn[n0 + i] - nm);
+            mn[n0 + i] = nm;
+          }
+        }
+      }
+      if (own) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) z[n] += ex2(fmaf(s[n], a.c, -mn[n]));
+      }
+      t += 2;
+      while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
+    if (et == 0) FKV_TRACE(3);
     flush_upto(nlp);
+    if (et == 0) FKV_TRACE(4);
 
     // ---------------- grid barrier: every CTA's partials are visible ---------------------------
     __threadfence();
+    tc_fence_before();
+    if (et == 0) FKV_TRACE(13);
     named_bar(2, kEpiThreads);
     if (et == 0) {
+      FKV_TRACE(14);
       atomicAdd(a.sync_counter, 1u);
       unsigned int seen;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sync_counter) : "memory");
-        if (seen < (unsigned)grid) __nanosleep(64);
       } while (seen < (unsigned)grid);
     }
     named_bar(2, kEpiThreads);
+    tc_fence_after();
+    if (et == 0) FKV_TRACE(5);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
+    // 8 lanes per row; every lane first issues all of its (up to 4) partial loads, then merges.
     for (int idx = et; idx < nlp * N * 8; idx += kEpiThreads) {
       const int sub = idx & 7, n = (idx >> 3) % N, lp = (idx >> 3) / N;
       const int pair = pair0 + lp;
@@ -365,12 +470,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       const long long ue = ub + a.n_tiles - 1;
       const int c_lo = cta_of_unit(ub, a.U, grid), c_hi = cta_of_unit(ue, a.U, grid);
       float M = kEmptyMax, Z = 0.f;
-      for (int c = c_lo + sub; c <= c_hi; c += 8) {
-        const int lpc = pair - unit_begin(c, a.U, grid) / a.n_tiles;
-        const float2 v = __ldcg(a.part + ((size_t)c * a.maxlp + lpc) * N + n);
-        const float nm = fmaxf(M, v.x);
-        Z = Z * ex2(M - nm) + v.y * ex2(v.x - nm);
-        M = nm;
+      for (int c0 = c_lo + sub; c0 <= c_hi; c0 += 32) {
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = c0 + 8 * i;
+          v[i] = make_float2(kEmptyMax, 0.f);
+          if (c <= c_hi) {
+            const int lpc = pair - unit_begin(c, a.U, grid) / a.n_tiles;
+            v[i] = __ldcg(a.part + ((size_t)c * a.maxlp + lpc) * N + n);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float nm = fmaxf(M, v[i].x);
+          Z = Z * ex2(M - nm) + v[i].y * ex2(v[i].x - nm);
+          M = nm;
+        }
       }
 #pragma unroll
       for (int o = 1; o < 8; o <<= 1) {
@@ -382,38 +498,50 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       if (sub == 0) colstat[lp * N + n] = make_float2(M, 1.0f / Z);
     }
     named_bar(2, kEpiThreads);
+    if (et == 0) FKV_TRACE(6);
 
     // ---------------- pass 2: votes -> pool -> group sum -> score ------------------------------
-    // continue the same job sequence: this warpgroup owns jobs j = wg, wg+2, ...
-    // (j left the pass-1 loop as the first own job index >= T)
+    // tiles in descending order; the first min(T, NB) of them are still resident in TMEM
     const float pad = (a.pooling == FKV_POOL_MAX) ? -INFINITY : 0.f;
-    for (; j < njobs; j += 2) {
-      const int u = u0 + (2 * T - 1 - j);
-      const int pair = u / a.n_tiles, t = u - pair * a.n_tiles;
+    const float inv_ks = 1.0f / (float)a.ks;
+    int cur_lp = -1, b = 0, kvl = 0;
+    { const int u = u0 + T - 1 - wg; pair = u >= 0 ? u / a.n_tiles : 0; t = u - pair * a.n_tiles; }
+    for (int j2 = wg; j2 < T; j2 += 2) {
+      const int lt = T - 1 - j2;
       const int lp = pair - pair0;
-      const int b = pair / a.nkv, kvl = pair % a.nkv;
-      mbar_wait(bar_tfull(wg), (j >> 1) & 1);
+      const int blk = lt & (NB - 1);
+      if (lp != cur_lp) {                            // (max, 1/sum) of this pair's rows -> registers
+        cur_lp = lp;
+        b = pair / a.nkv; kvl = pair - b * a.nkv;
+#pragma unroll
+        for (int n = 0; n < N; ++n) { const float2 v = colstat[lp * N + n]; mn[n] = v.x; z[n] = v.y; }
+      }
+      if (j2 >= NB) {                                // recomputed tile: wait for its MMA
+        const int fill = 2 * fills_pass1(blk) - 2 - lt / NB;
+        mbar_wait(bar_tfull(blk), fill & 1);
+      }
       tc_fence_after();
+      if (et == 0) FKV_TRACE2(4, j2 >> 1);
       float s[N];
-      tmem_load_row<N>(tmem_base + ((uint32_t)(quarter * 32) << 16) + wg * NMMA, s);
+      tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
+      if (et == 0) FKV_TRACE2(5, j2 >> 1);
       tc_fence_before();
-      mbar_arrive(bar_tempty(wg));
+      mbar_arrive(j2 >= NB ? bar_tempty(blk) : bar_rdone(blk));
       const int key = t * a.S - a.half + row;
       const bool in_prefix = (key >= 0) && (key < a.P);
-      float* vb = vbuf + ((wg * 2 + ((j >> 1) & 1)) * G) * kTile;
-      const float2* cs = colstat + lp * N;
+      float* vb = vbuf + ((wg * 2 + ((j2 >> 1) & 1)) * G) * kTile;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float vote = 0.f;
 #pragma unroll
-        for (int r = 0; r < W; ++r) {
-          const float2 mz = cs[g * W + r];
-          vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mz.x)), mz.y, vote);   // rows summed in order (utils.py:104)
-        }
+        for (int r = 0; r < W; ++r)                  // rows summed in order (utils.py:104)
+          vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mn[g * W + r])), z[g * W + r], vote);
         vb[g * kTile + row] = in_prefix ? vote : pad;
       }
+      if (et == 0) FKV_TRACE2(6, j2 >> 1);
       named_bar(3 + wg, 128);
+      if (et == 0) FKV_TRACE2(7, j2 >> 1);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
       if (own) {
         float acc = 0.f;
@@ -425,21 +553,35 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             for (int d = -a.half; d <= a.half; ++d) pooled = fmaxf(pooled, vb[g * kTile + row + d]);
           } else {
             float sum = 0.f;
-            for (int d = -a.half; d <= a.half; ++d) sum += vb[g * kTile + row + d];
-            pooled = sum / (float)a.ks;               // count_include_pad: always / kernel_size
+            const float* vr = vb + g * kTile + row;
+            if (a.half == 3) {                        // kernel_size 7 (the reference default), unrolled
+#pragma unroll
+              for (int d = -3; d <= 3; ++d) sum += vr[d];
+            } else if (a.half == 2) {
+#pragma unroll
+              for (int d = -2; d <= 2; ++d) sum += vr[d];
+            } else {
+              for (int d = -a.half; d <= a.half; ++d) sum += vr[d];
+            }
+            pooled = sum * inv_ks;                    // count_include_pad: always / kernel_size
           }
           if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
           else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * G + g - a.out_h0) * a.score_sh + key] = pooled;
         }
         if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
       }
+      if (et == 0) FKV_TRACE2(8, j2 >> 1);
+      t -= 2;
+      while (t < 0) { t += a.n_tiles; --pair; }
     }
   }
 
+  if (threadIdx.x == 64) FKV_TRACE(7);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 64) FKV_TRACE(8);
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }
 
@@ -537,8 +679,7 @@ Plan make_plan(const fkv_score_params& p) {
   const int NMMA = pl.N < 16 ? 16 : pl.N;
   const size_t tile_bytes = (size_t)kTile * p.D * 2;
   const size_t q_bytes = ((size_t)NMMA * p.D * 2 + 1023) & ~(size_t)1023;
-  const size_t misc = 24 * 8 + 16 + (size_t)8 * pl.N * 4 + (size_t)8 * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 +
-                      (size_t)pl.N * 4 + (size_t)2 * 2 * pl.G * kTile * 4;
+  const size_t misc = 112 * 8 + 16 + (size_t)8 * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)2 * 2 * pl.G * kTile * 4;
   const size_t budget = 227 * 1024 - 1024 - 2 * q_bytes - misc - 256;
   int nst = (int)(budget / tile_bytes);
   if (nst > kMaxStages) nst = kMaxStages;
@@ -596,13 +737,39 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   if ((rc = make_map(&mk, p.k, p.dtype, p.B, p.Hkv, p.L, p.D, kTile, &a.kpos_l, &a.kpos_h, &a.kpos_b)) != FKV_OK) return rc;
   if ((rc = make_map(&mq, p.q, p.dtype, p.B, p.Hq, p.L, p.D, pl.W, &a.qpos_l, &a.qpos_h, &a.qpos_b)) != FKV_OK) return rc;
   FKV_CUDA_TRY(cudaMemsetAsync(a.sync_counter, 0, 4, s));
+  static const bool trace_on = getenv("FKV_TC_TRACE") != nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  if (trace_on) {
+    if (!trace_buf) FKV_CUDA_TRY(cudaMalloc(&trace_buf, (256 * 16 + 1024) * sizeof(unsigned long long)));
+    a.trace = trace_buf;
+  }
 
 #define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) return launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
+  int rc_launch = FKV_EMODE;
+#undef FKV_TC_CASE
+#define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) rc_launch = launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
   FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4); FKV_TC_CASE(8, 8);
   FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2); FKV_TC_CASE(16, 4);
   FKV_TC_CASE(32, 1); FKV_TC_CASE(32, 2);
 #undef FKV_TC_CASE
-  return FKV_EMODE;
+  if (trace_on && rc_launch == FKV_OK) {                // debugging aid only: synchronises and prints phase times
+    cudaStreamSynchronize(s);
+    static unsigned long long host[256 * 16 + 1024];
+    cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < pl.grid; ++c) if (host[c * 16] < t0) t0 = host[c * 16];
+    const char* names[15] = {"start", "setup", "first_acc", "pass1_end", "flushed", "grid_bar", "colstat", "pass2_end", "exit", "mma_p1_end", "tma_p1_end", "fl_shfl", "fl_bar1", "gb_fence", "gb_bar1"};
+    for (int sidx = 0; sidx < 15; ++sidx) {
+      unsigned long long mn = ~0ull, mx = 0; double avg = 0;
+      for (int c = 0; c < pl.grid; ++c) { unsigned long long v = host[c * 16 + sidx] - t0; if (v < mn) mn = v; if (v > mx) mx = v; avg += v; }
+      if (sidx == 0) for (int m = 0; m < 16; ++m) fprintf(stderr, "[fkv tile %2d] tma_issue %7.2f  mma_full %7.2f  mma_commit %7.2f  epi_tfull %7.2f\n", m,
+          (host[4096 + m] - t0) / 1e3, (host[4096 + 64 + m] - t0) / 1e3, (host[4096 + 128 + m] - t0) / 1e3, (host[4096 + 192 + m] - t0) / 1e3);
+      if (sidx == 0) for (int m = 0; m < 8; ++m) fprintf(stderr, "[fkv p2 tile %2d] start %7.2f  tmem_ld %7.2f  votes %7.2f  bar %7.2f  pooled %7.2f\n", m,
+          (host[4096 + 256 + m] - t0) / 1e3, (host[4096 + 320 + m] - t0) / 1e3, (host[4096 + 384 + m] - t0) / 1e3, (host[4096 + 448 + m] - t0) / 1e3, (host[4096 + 512 + m] - t0) / 1e3);
+      fprintf(stderr, "[fkv trace] L=%d grid=%d %-10s min %8.2f us  avg %8.2f us  max %8.2f us\n", p.L, pl.grid, names[sidx], mn / 1e3, avg / pl.grid / 1e3, mx / 1e3);
+    }
+  }
+  return rc_launch;
 }
 
 }  // namespace fkv
