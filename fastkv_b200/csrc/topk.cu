@@ -2,15 +2,29 @@
 // and the global TSP selection.  Replaces Tensor.topk / sum+topk+cat+sort at
 // baselines/fastkv/utils.py:113 and :127-130.
 //
-// One 1024-thread CTA per row:
-//   phase 0  (nsum > 1) fixed-order sum of the source rows -> dense fp32 row (TSP importance)
-//   phase 1  MSD radix select on order-preserving uint32 keys, digits 12 + 12 + 8 bits, each pass
-//            filtering on the prefix found so far -> exact threshold key tau and the number of
-//            tau-valued elements still needed
-//   phase 2  index-ordered compaction (block scan): every key > tau plus the first `need` keys
-//            == tau in index order  -> the selected set, ascending by index
-//   phase 3  VALUE_DESC only: bitonic sort of (key, ~index) composites in shared memory
+// Two kernels:
+//  * topk_cluster_kernel — the fast path (n <= 131072, k <= 4096).  One thread-block CLUSTER of
+//    C = ceil(n / 16384) CTAs per row; each CTA keeps its slice of the row in registers (16 values
+//    per thread), so the row is read from L2/HBM exactly once.
+//      1. local 4096-bin histogram of the top 12 key bits (shared-memory atomics)
+//      2. histograms are reduced across the cluster through distributed shared memory (each CTA
+//         owns 4096/C bins), the owner of the bin holding the k-th largest value finds it
+//      3. every key in or above that bin (k <= count <= 4096, else fall back) is sent to the
+//         leader CTA's shared memory (DSMEM stores)
+//      4. the leader ranks the candidates without a sort: counting-scatter by bin, then each
+//         candidate counts the larger keys inside its own (small) bin -> final position
+//      5. INDEX_ASC (TSP): the k-th composite key is broadcast and every CTA compacts its own
+//         selected indices in index order (block scan + cluster prefix)
+//  * topk_row_kernel — generic fallback (any n, any k, heavy ties): one CTA per row, MSD radix
+//    select (12 + 12 + 8 bits) over global memory, index-ordered compaction, bitonic sort.
+#include <cooperative_groups.h>
+
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace fkv {
 namespace {
@@ -19,6 +33,8 @@ constexpr int kThreads = 1024;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxBins = 4096;
 constexpr int kSmemSortMax = 16384;              // composites kept in shared memory (128 KB)
+constexpr int kMaxCluster = 8;
+constexpr int kCandMax = 4096;
 
 __device__ inline uint32_t ordered_key(float x) {
   x += 0.0f;                                      // -0.0 -> +0.0 so both zeros compare equal
@@ -33,10 +49,13 @@ struct TopkArgs {
   float* dense;            // [rows][n] summed rows (workspace or imp_out) when nsum > 1
   unsigned long long* sort_ws;   // [rows][pow2(k)] global sort scratch when k > kSmemSortMax
   int sort_cap;            // pow2 >= k
+  int cluster;             // CTAs per row (cluster path)
+  int write_dense;         // cluster path: also store the summed row (importance output)
+  unsigned long long* trace;   // FKV_TOPK_TRACE debugging aid
 };
 
 // Inclusive block scan of one uint32 per thread (kThreads threads); returns inclusive value and
-// the block total through `total`.  `wsum` is kWarps+1 words of shared scratch.
+// the block total through `total`.  `wsum` is kWarps words of shared scratch.
 __device__ inline uint32_t block_scan_incl(uint32_t v, uint32_t* wsum, uint32_t& total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -61,37 +80,14 @@ __device__ inline uint32_t block_scan_incl(uint32_t v, uint32_t* wsum, uint32_t&
   return v + (warp ? wsum[warp - 1] : 0u);
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
-topk_row_kernel(TopkArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);                    // [4096]
-  uint32_t* wsum = hist + kMaxBins;                                          // [32]
-  uint32_t* bc = wsum + kWarps;                                              // [4] broadcast slots
-  unsigned long long* sort_smem = reinterpret_cast<unsigned long long*>(bc + 4);
-
-  const int row = blockIdx.x, tid = threadIdx.x;
-  const int n = a.n, k = a.k;
-  int64_t* out = a.out + (int64_t)row * a.out_stride_row;
-
-  // ---- phase 0: fixed-order head sum (baselines/fastkv/utils.py:127) -----------------------------
-  const float* x;
-  if (a.nsum > 1) {
-    float* dense = a.dense + (int64_t)row * n;
-    const float* base = a.src + (int64_t)row * a.src_stride_row;
-    for (int j = tid; j < n; j += kThreads) {
-      float acc = base[j];
-      for (int s = 1; s < a.nsum; ++s) acc += base[(int64_t)s * a.src_stride_sum + j];
-      dense[j] = acc;
-    }
-    __syncthreads();
-    x = dense;
-  } else {
-    x = a.src + (int64_t)row * a.src_stride_row;
-  }
-
-  // ---- phase 1: radix select ----------------------------------------------------------------------
+// ---- generic single-CTA selection over a row in global memory ---------------------------------------
+__device__ void select_row_generic(const float* __restrict__ x, int n, int k, int order, int tail,
+                                   int64_t* __restrict__ out, uint32_t* hist, uint32_t* wsum, uint32_t* bc,
+                                   unsigned long long* comp, int sort_cap) {
+  const int tid = threadIdx.x;
+  // ---- radix select: exact threshold key tau + number of tau-valued keys still needed -----------
   uint32_t prefix = 0, prefix_mask = 0;
-  uint32_t need = (uint32_t)k;                     // elements still to take inside the current prefix
+  uint32_t need = (uint32_t)k;
   if (k < n) {
     const int shifts[3] = {20, 8, 0};
     const int bits[3] = {12, 12, 8};
@@ -151,17 +147,14 @@ topk_row_kernel(TopkArgs a) {
       __syncthreads();
     }
   } else {
-    prefix = 0; prefix_mask = 0xffffffffu; need = 0;   // k == n: everything is "greater" than tau = 0 key
+    prefix = 0; prefix_mask = 0xffffffffu; need = 0;
   }
   const uint32_t tau = prefix;
   const bool take_all = (k >= n);
 
-  // ---- phase 2: index-ordered compaction ----------------------------------------------------------
-  const bool by_value = (a.order == FKV_ORDER_VALUE_DESC);
-  unsigned long long* comp = nullptr;
-  if (by_value) comp = (a.sort_cap <= kSmemSortMax) ? sort_smem : a.sort_ws + (int64_t)row * a.sort_cap;
-
-  uint32_t base_gt = 0, base_eq = 0;                 // selected-so-far counts
+  // ---- index-ordered compaction ---------------------------------------------------------------------
+  const bool by_value = (order == FKV_ORDER_VALUE_DESC);
+  uint32_t base_gt = 0, base_eq = 0;
   for (int j0 = 0; j0 < n; j0 += kThreads * 4) {
     const int j = j0 + tid * 4;
     uint32_t key[4];
@@ -195,12 +188,12 @@ topk_row_kernel(TopkArgs a) {
   }
 
   if (!by_value) {
-    for (int i = tid; i < a.tail; i += kThreads) out[k + i] = (int64_t)(n + i);
+    for (int i = tid; i < tail; i += kThreads) out[k + i] = (int64_t)(n + i);
     return;
   }
 
-  // ---- phase 3: bitonic sort, descending on (key, ~index) -------------------------------------------
-  const int cap = a.sort_cap;
+  // ---- bitonic sort, descending on (key, ~index) ------------------------------------------------------
+  const int cap = sort_cap;
   for (int i = k + tid; i < cap; i += kThreads) comp[i] = 0ull;      // padding sorts last
   __syncthreads();
   for (int size = 2; size <= cap; size <<= 1) {
@@ -216,7 +209,390 @@ topk_row_kernel(TopkArgs a) {
     }
   }
   for (int i = tid; i < k; i += kThreads) out[i] = (int64_t)(0xffffffffu - (uint32_t)(comp[i] & 0xffffffffull));
-  for (int i = tid; i < a.tail; i += kThreads) out[k + i] = (int64_t)(n + i);
+  for (int i = tid; i < tail; i += kThreads) out[k + i] = (int64_t)(n + i);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+topk_row_kernel(TopkArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* hist = reinterpret_cast<uint32_t*>(smem_raw);                    // [4096]
+  uint32_t* wsum = hist + kMaxBins;                                          // [32]
+  uint32_t* bc = wsum + kWarps;                                              // [4] broadcast slots
+  unsigned long long* sort_smem = reinterpret_cast<unsigned long long*>(bc + 4);
+
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n;
+  int64_t* out = a.out + (int64_t)row * a.out_stride_row;
+
+  // fixed-order head sum (baselines/fastkv/utils.py:127)
+  const float* x;
+  if (a.nsum > 1) {
+    float* dense = a.dense + (int64_t)row * n;
+    const float* base = a.src + (int64_t)row * a.src_stride_row;
+    for (int j = tid; j < n; j += kThreads) {
+      float acc = base[j];
+      for (int s = 1; s < a.nsum; ++s) acc += base[(int64_t)s * a.src_stride_sum + j];
+      dense[j] = acc;
+    }
+    __syncthreads();
+    x = dense;
+  } else {
+    x = a.src + (int64_t)row * a.src_stride_row;
+  }
+  unsigned long long* comp = nullptr;
+  if (a.order == FKV_ORDER_VALUE_DESC)
+    comp = (a.sort_cap <= kSmemSortMax) ? sort_smem : a.sort_ws + (int64_t)row * a.sort_cap;
+  select_row_generic(x, n, a.k, a.order, a.tail, out, hist, wsum, bc, comp, a.sort_cap);
+}
+
+// ---- cluster fast path -------------------------------------------------------------------------------
+constexpr int kSliceKeys = 32768;                 // keys per CTA, held in shared memory
+constexpr int kKeysPadded = kSliceKeys + kSliceKeys / 32;   // one pad word per 32 keys: conflict-free blocked reads
+constexpr int kSortHalf = 2048;                   // capacity of each of the two sort regions
+
+struct ClusterSmem {
+  uint32_t keys[kKeysPadded];       // order-preserving keys of this CTA's slice
+  uint32_t hist[kMaxBins];          // local 12-bit histogram; leader: second-level histogram
+  unsigned long long cand[kCandMax];     // leader: gathered candidates (unordered)
+  unsigned long long sortbuf[kCandMax];  // leader: candidates grouped by adaptive bin (also the generic path's sort buffer)
+  uint16_t bbase[kMaxBins];         // leader: candidates in higher adaptive bins (<= 4096)
+  uint32_t sub[kMaxCluster];        // per-owner subtotals
+  uint32_t cnt_cta[kMaxCluster];    // INDEX_ASC: selected count per CTA
+  uint32_t wsum[kWarps];
+  uint32_t bc[12];                  // [0] bin*, [1] count above bin*, [2] count in bin*, [3] gather cursor,
+                                    // [4..5] k-th composite (lo, hi), [6] sub-bin*, [7] nA cursor, [8] nB cursor, [9] need in sub-bin
+};
+
+__device__ inline int key_slot(int i) { return i + (i >> 5); }
+
+// bitonic sort of `cap` (power of two) composites, descending; all kThreads threads participate
+__device__ inline void bitonic_desc(unsigned long long* buf, int cap) {
+  const int tid = threadIdx.x;
+  for (int size = 2; size <= cap; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < cap / 2; t += kThreads) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long va = buf[lo], vb = buf[hi];
+        if ((va < vb) == desc) { buf[lo] = vb; buf[hi] = va; }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+#define TK_TRACE(i) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[i] = t_; } } while (0)
+
+__global__ void __launch_bounds__(kThreads, 1)
+topk_cluster_kernel(TopkArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ClusterSmem& sm = *reinterpret_cast<ClusterSmem*>(smem_raw);
+  TK_TRACE(0);
+  cg::cluster_group cluster = cg::this_cluster();
+  const int C = a.cluster;
+  const bool multi = C > 1;                         // C == 1: plain CTA, no cluster traffic at all
+  const int crank = multi ? (int)cluster.block_rank() : 0;
+  const int row = blockIdx.x / C;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n = a.n, k = a.k;
+  int64_t* out = a.out + (int64_t)row * a.out_stride_row;
+  auto csync = [&]() { if (multi) cluster.sync(); else __syncthreads(); };
+
+  for (int i = tid; i < kMaxBins; i += kThreads) sm.hist[i] = 0;
+  if (tid < 12) sm.bc[tid] = 0;
+  __syncthreads();
+
+  // ---- 1. load the slice (fixed-order head sum for TSP), keys -> smem, 12-bit histogram ---------------
+  const int per_cta = ((n + C - 1) / C + 3) & ~3;
+  const int base = crank * per_cta;
+  const int cnt = max(0, min(n, base + per_cta) - base);       // keys of this CTA
+  const float* src = a.src + (int64_t)row * a.src_stride_row;
+  {
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(src) | (uintptr_t)(a.src_stride_sum * 4)) & 15) == 0;
+    float* dense = a.write_dense ? a.dense + (int64_t)row * n : nullptr;
+    auto emit = [&](int i, float x0, float x1, float x2, float x3) {   // 4 consecutive keys -> smem (+ dense row)
+      const float x[4] = {x0, x1, x2, x3};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (i + e < cnt) {
+          if (dense) dense[base + i + e] = x[e];
+          sm.keys[key_slot(i + e)] = ordered_key(x[e]);
+        }
+    };
+    auto load4 = [&](const float* p, int i, float4& r) {                // p: row base, keys [i, i+4) of the slice
+      if (vec_ok && i + 3 < cnt) r = *reinterpret_cast<const float4*>(p + base + i);
+      else {
+        r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < cnt) r.x = p[base + i];
+        if (i + 1 < cnt) r.y = p[base + i + 1];
+        if (i + 2 < cnt) r.z = p[base + i + 2];
+        if (i + 3 < cnt) r.w = p[base + i + 3];
+      }
+    };
+    if (a.nsum == 1) {
+      constexpr int U = 4;                          // float4 loads in flight per thread
+      for (int i0 = tid * 4; i0 < cnt; i0 += kThreads * 4 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) load4(src, i0 + u * kThreads * 4, v[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) emit(i0 + u * kThreads * 4, v[u].x, v[u].y, v[u].z, v[u].w);
+      }
+    } else {
+      for (int i = tid * 4; i < cnt; i += kThreads * 4) {
+        float4 acc;
+        load4(src, i, acc);
+        for (int h0 = 1; h0 < a.nsum; h0 += 4) {    // fixed head order (utils.py:127), 4 loads in flight
+          float4 t4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (h0 + q < a.nsum) load4(src + (int64_t)(h0 + q) * a.src_stride_sum, i, t4[q]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (h0 + q < a.nsum) { acc.x += t4[q].x; acc.y += t4[q].y; acc.z += t4[q].z; acc.w += t4[q].w; }
+        }
+        emit(i, acc.x, acc.y, acc.z, acc.w);
+      }
+    }
+  }
+  __syncthreads();
+  // 12-bit histogram with run-length aggregation: neighbouring keys usually share a bin, so a warp
+  // issues one shared-memory atomic per run instead of one per key
+  for (int i0 = 0; i0 < cnt; i0 += kThreads) {
+    const int i = i0 + tid;
+    const uint32_t bin = (i < cnt) ? (sm.keys[key_slot(i)] >> 20) : 0xffffffffu;
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
+    const bool head = (lane == 0) || (bin != prev);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    if (head && i < cnt) {
+      const uint32_t rest = (lane == 31) ? 0u : (heads >> (lane + 1));
+      const int len = rest ? (__ffs(rest)) : (32 - lane);
+      atomicAdd(&sm.hist[bin], (uint32_t)len);
+    }
+  }
+  TK_TRACE(1);
+  csync();
+  TK_TRACE(2);
+
+  // ---- 2. reduce histograms (owner = CTA crank for bins [crank*nbo, (crank+1)*nbo)), find bin* --------
+  const int nbo = kMaxBins / C;
+  uint32_t my_tot[4] = {0, 0, 0, 0};                // owned bins, top-down: b = hi - (4 tid + i)
+  uint32_t lsum = 0;
+  const int hi = (crank + 1) * nbo - 1;
+  if (multi) {
+    uint32_t part[4][kMaxCluster];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < kMaxCluster; ++c)
+        part[i][c] = (tid * 4 + i < nbo && c < C) ? cluster.map_shared_rank(sm.hist, c)[hi - (tid * 4 + i)] : 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int c = 0; c < kMaxCluster; ++c) my_tot[i] += part[i][c];
+      lsum += my_tot[i];
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { my_tot[i] = sm.hist[hi - (tid * 4 + i)]; lsum += my_tot[i]; }
+  }
+  uint32_t own_total;
+  const uint32_t incl = block_scan_incl(lsum, sm.wsum, own_total);
+  if (multi) {
+    if (tid < C) cluster.map_shared_rank(sm.sub, tid)[crank] = own_total;
+    cluster.sync();
+  }
+  {
+    uint32_t above_owner = 0;
+    for (int c = C - 1; c > crank; --c) above_owner += sm.sub[c];
+    const uint32_t excl = above_owner + incl - lsum;
+    if (excl < (uint32_t)k && (uint32_t)k <= excl + lsum) {    // the k-th key is in one of my 4 bins
+      uint32_t above = excl;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (above < (uint32_t)k && (uint32_t)k <= above + my_tot[i]) {
+          for (int c = 0; c < C; ++c) {
+            uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, c) : sm.bc;
+            rbc[0] = (uint32_t)(hi - (tid * 4 + i));
+            rbc[1] = above;
+            rbc[2] = my_tot[i];
+          }
+        }
+        above += my_tot[i];
+      }
+    }
+  }
+  csync();
+  TK_TRACE(3);
+  const uint32_t bin_star = sm.bc[0];
+  const uint32_t n_above = sm.bc[1];
+  const uint32_t n_cand = n_above + sm.bc[2];
+  const bool by_value = (a.order == FKV_ORDER_VALUE_DESC);
+
+  if (n_cand > (uint32_t)kCandMax) {
+  fallback:
+    // heavy ties / very flat rows: the leader re-selects from global memory with the generic path
+    if (a.write_dense) __threadfence();
+    csync();                                        // dense row (if any) fully written, remote smem no longer needed
+    if (crank == 0) {
+      const float* x = (a.nsum > 1) ? a.dense + (int64_t)row * n : src;
+      select_row_generic(x, n, k, a.order, a.tail, out, sm.hist, sm.wsum, sm.bc, sm.sortbuf, a.sort_cap);
+    }
+    return;
+  }
+
+  // ---- 3. send candidates (bin >= bin*) to the leader -------------------------------------------------
+  {
+    uint32_t* cursor = multi ? &cluster.map_shared_rank(sm.bc, 0)[3] : &sm.bc[3];
+    unsigned long long* lcand = multi ? cluster.map_shared_rank(sm.cand, 0) : sm.cand;
+    // pass 1: how many candidates does this warp hold?  pass 2: one cursor atomic per warp, then write
+    uint32_t wcount = 0;
+    for (int i0 = 0; i0 < cnt; i0 += kThreads) {
+      const int i = i0 + tid;
+      const bool take = (i < cnt) && ((sm.keys[key_slot(i)] >> 20) >= bin_star);
+      wcount += __popc(__ballot_sync(0xffffffffu, take));
+    }
+    uint32_t wbase = 0;
+    if (lane == 0 && wcount) wbase = atomicAdd(cursor, wcount);
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    for (int i0 = 0; i0 < cnt; i0 += kThreads) {
+      const int i = i0 + tid;
+      const uint32_t key = (i < cnt) ? sm.keys[key_slot(i)] : 0u;
+      const bool take = (i < cnt) && ((key >> 20) >= bin_star);
+      const uint32_t m = __ballot_sync(0xffffffffu, take);
+      if (take)
+        lcand[wbase + __popc(m & ((1u << lane) - 1))] =
+            ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
+      wbase += __popc(m);
+    }
+  }
+  csync();
+  TK_TRACE(4);
+
+  // ---- 4. leader: rank the candidates without a general sort ------------------------------------------
+  // Counting scatter on 4096 ADAPTIVE bins (the candidates' key range [bin* << 20, max key] mapped
+  // linearly onto the bins, so a bin holds ~1 key), then every candidate counts the larger keys in
+  // its own bin: rank = keys in higher bins + larger keys in the bin.  A skewed row (a bin with
+  // more than 64 keys, e.g. exact ties) takes the bitonic sort instead.
+  if (crank == 0) {
+    uint32_t* cursor = sm.hist;
+    uint16_t* bbase = sm.bbase;                                         // keys in higher bins
+    unsigned long long* grouped = sm.sortbuf;
+    // block max of the candidate keys
+    uint32_t kmax = 0;
+    for (int i = tid; i < (int)n_cand; i += kThreads) kmax = max(kmax, (uint32_t)(sm.cand[i] >> 32));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
+    if (lane == 0) sm.wsum[tid >> 5] = kmax;
+    __syncthreads();
+    kmax = sm.wsum[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    const uint32_t klo = bin_star << 20;
+    const unsigned long long range = (unsigned long long)(kmax - klo) + 1ull;
+    const unsigned long long mult = (((unsigned long long)kMaxBins << 32) - 1ull) / range;   // bin = ((key-klo)*mult) >> 32 < 4096
+    auto fine_bin = [&](uint32_t key) { return (uint32_t)(((unsigned long long)(key - klo) * mult) >> 32); };
+    __syncthreads();
+    for (int i = tid; i < (int)n_cand; i += kThreads) atomicAdd(&cursor[fine_bin((uint32_t)(sm.cand[i] >> 32))], 1u);
+    __syncthreads();
+    bool skew;
+    {
+      uint32_t local[4], ls = 0, mx = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { local[i] = cursor[kMaxBins - 1 - (tid * 4 + i)]; ls += local[i]; mx = max(mx, local[i]); }
+      skew = __syncthreads_or(mx > 64u);
+      uint32_t total;
+      const uint32_t inc = block_scan_incl(ls, sm.wsum, total);
+      uint32_t above = inc - ls;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int b = kMaxBins - 1 - (tid * 4 + i);
+        bbase[b] = (uint16_t)above;
+        above += local[i];
+      }
+    }
+    __syncthreads();
+    unsigned long long kth = 0ull;
+    if (!skew) {
+      {
+        for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
+        __syncthreads();
+        for (int i = tid; i < (int)n_cand; i += kThreads) {
+          const unsigned long long c = sm.cand[i];
+          const uint32_t b = fine_bin((uint32_t)(c >> 32));
+          grouped[bbase[b] + atomicAdd(&cursor[b], 1u)] = c;
+        }
+        __syncthreads();
+        for (int i = tid; i < (int)n_cand; i += kThreads) {
+          const unsigned long long c = grouped[i];
+          const uint32_t b = fine_bin((uint32_t)(c >> 32));
+          const uint32_t s0 = bbase[b], s1 = s0 + cursor[b];
+          uint32_t rank = s0;
+          for (uint32_t q = s0; q < s1; ++q) rank += (grouped[q] > c);
+          if (rank < (uint32_t)k) {
+            if (by_value) out[rank] = (int64_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
+            if (rank == (uint32_t)k - 1) { sm.bc[4] = (uint32_t)(c & 0xffffffffull); sm.bc[5] = (uint32_t)(c >> 32); }
+          }
+        }
+        __syncthreads();
+        kth = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
+      }
+    }
+    if (skew) {
+      int cap = 1;
+      while (cap < (int)n_cand) cap <<= 1;
+      for (int i = (int)n_cand + tid; i < cap; i += kThreads) sm.cand[i] = 0ull;
+      __syncthreads();
+      bitonic_desc(sm.cand, cap);
+      if (by_value)
+        for (int i = tid; i < k; i += kThreads) out[i] = (int64_t)(0xffffffffu - (uint32_t)(sm.cand[i] & 0xffffffffull));
+      kth = sm.cand[k - 1];
+    }
+    if (by_value) {
+      for (int i = tid; i < a.tail; i += kThreads) out[k + i] = (int64_t)(n + i);
+    } else if (tid == 0) {
+      for (int cc = 0; cc < C; ++cc) {
+        uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, cc) : sm.bc;
+        rbc[4] = (uint32_t)(kth & 0xffffffffull);
+        rbc[5] = (uint32_t)(kth >> 32);
+      }
+    }
+  }
+  TK_TRACE(5);
+  csync();
+  if (sm.bc[11]) goto fallback;                     // uniform across the cluster
+  if (by_value) return;
+
+  // ---- 5. INDEX_ASC: every CTA compacts its own selected keys in index order ---------------------------
+  const unsigned long long thr = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
+  constexpr int kPerThread = kSliceKeys / kThreads;               // 32 consecutive keys per thread
+  uint32_t mine = 0;
+  uint32_t selmask = 0;
+#pragma unroll
+  for (int e = 0; e < kPerThread; ++e) {
+    const int i = tid * kPerThread + e;
+    if (i < cnt) {
+      const unsigned long long c = ((unsigned long long)sm.keys[key_slot(i)] << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
+      if (c >= thr) { ++mine; selmask |= 1u << e; }
+    }
+  }
+  uint32_t cta_total;
+  const uint32_t inc = block_scan_incl(mine, sm.wsum, cta_total);
+  uint32_t pos = inc - mine;
+  if (multi) {
+    if (tid < C) cluster.map_shared_rank(sm.cnt_cta, tid)[crank] = cta_total;
+    cluster.sync();
+    for (int c = 0; c < crank; ++c) pos += sm.cnt_cta[c];
+  }
+#pragma unroll
+  for (int e = 0; e < kPerThread; ++e)
+    if (selmask & (1u << e)) out[pos++] = (int64_t)(base + tid * kPerThread + e);
+  if (crank == 0)
+    for (int i = tid; i < a.tail; i += kThreads) out[k + i] = (int64_t)(n + i);
+  TK_TRACE(6);
+  if (multi) cluster.sync();                        // keep this CTA's smem alive until all remote accesses finished
 }
 
 inline int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -247,6 +623,55 @@ int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
     }
   }
   const bool by_value = p.order == FKV_ORDER_VALUE_DESC;
+
+  static const bool no_cluster = getenv("FKV_TOPK_NO_CLUSTER") != nullptr;
+  // CTAs per row: enough for the slice to fit (32768 keys per CTA) and, for summed rows (TSP), enough
+  // to spread the nsum-fold read over several SMs
+  int C = ceil_div(p.n, kSliceKeys);
+  if (a.nsum > 1 && C <= kMaxCluster) {
+    const long long want = ((long long)p.n * a.nsum + kSliceKeys - 1) / kSliceKeys;
+    C = (int)(want > kMaxCluster ? kMaxCluster : (want > C ? want : C));
+  }
+  if (!no_cluster && C <= kMaxCluster && p.k <= kSortHalf && (p.src_stride_row % 4) == 0) {
+    int Cp = 1;
+    while (Cp < C) Cp <<= 1;                        // cluster sizes 1, 2, 4, 8 (divides the 4096 bins)
+    a.cluster = Cp;
+    a.write_dense = (a.nsum > 1);                   // the fallback inside the kernel needs the dense row
+    static bool attr_set = false;
+    if (!attr_set) {
+      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(ClusterSmem)));
+      attr_set = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(p.rows * Cp);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = sizeof(ClusterSmem);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = Cp; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static const bool trace_on = getenv("FKV_TOPK_TRACE") != nullptr;
+    static unsigned long long* trace_buf = nullptr;
+    if (trace_on) {
+      if (!trace_buf) FKV_CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long)));
+      a.trace = trace_buf;
+    }
+    FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, topk_cluster_kernel, a));
+    count_launch();
+    if (trace_on) {
+      cudaStreamSynchronize(s);
+      unsigned long long h[16];
+      cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[topk trace] n=%d rows=%d C=%d order=%d:", p.n, p.rows, Cp, p.order);
+      for (int i = 1; i <= 6; ++i) fprintf(stderr, " %d:%.2f", i, (double)(h[i] - h[0]) / 1e3);
+      fprintf(stderr, "\n");
+    }
+    return FKV_OK;
+  }
+
   size_t smem = (kMaxBins + kWarps + 4) * sizeof(uint32_t);
   if (by_value) {
     if (a.sort_cap <= kSmemSortMax) smem += (size_t)a.sort_cap * sizeof(unsigned long long);
@@ -256,11 +681,11 @@ int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
       a.sort_ws = reinterpret_cast<unsigned long long*>(ws + off);
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set_row = false;
+  if (!attr_set_row) {
     const int smem_max = (int)((kMaxBins + kWarps + 4) * sizeof(uint32_t) + (size_t)kSmemSortMax * sizeof(unsigned long long));
     FKV_CUDA_TRY(cudaFuncSetAttribute(topk_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    attr_set = true;
+    attr_set_row = true;
   }
   topk_row_kernel<<<p.rows, kThreads, smem, s>>>(a);
   FKV_LAUNCH_CHECK();
