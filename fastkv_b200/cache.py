@@ -1,0 +1,102 @@
+"""Pre-allocated compact KV cache (replaces HF ``DynamicCache`` on the FastKV path).
+
+The reference stores the compacted K/V in a ``DynamicCache`` whose ``update`` re-allocates and
+``torch.cat``s the whole layer cache on every decode step (baselines/fastkv/llama_model.py:142-145).
+Here every layer owns one ``[B, Hkv, capacity, D]`` buffer sized ``compact rows + max_new_tokens``:
+the prefill writes the compacted rows once, decode steps append one row in place
+(``fkv_cache_append``) and the decode-attention kernel reads rows ``[0, seq_len)``.
+
+``update()`` keeps HF's ``Cache.update`` calling convention so the patched attention forwards read
+like the reference's; ``get_seq_length()`` returns the layer-0 cache length exactly like
+``DynamicCache`` did for the reference's benchmark loop (benchmark/e2e.py:174 passes no position
+ids, so decode positions continue from the COMPACT length there).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+class CompactKVCache:
+    """HF-Cache-compatible (duck-typed) container of per-layer compact K/V buffers."""
+
+    is_compileable = False
+
+    def __init__(self, config=None, max_new_tokens: int = 256):
+        self.max_new_tokens = int(max_new_tokens)
+        self.k: List[Optional[torch.Tensor]] = []
+        self.v: List[Optional[torch.Tensor]] = []
+        self.seq_lens: List[int] = []                 # host mirror of the per-layer length
+        self.seq_lens_dev: List[Optional[torch.Tensor]] = []   # int32 [1] on device (CUDA-graph friendly)
+        self.true_length = 0                           # prompt length + generated tokens (not compacted)
+
+    # -- HF Cache surface -----------------------------------------------------------------------
+    def __len__(self):
+        return len(self.k)
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        if layer_idx >= len(self.seq_lens):
+            return 0
+        return self.seq_lens[layer_idx]
+
+    def get_mask_sizes(self, cache_position=None, layer_idx: int = 0):   # transformers >= 4.5x mask helpers
+        q = int(cache_position.shape[0]) if cache_position is not None else 1
+        return self.get_seq_length(layer_idx) + q, 0
+
+    def _grow_lists(self, layer_idx: int):
+        while len(self.k) <= layer_idx:
+            self.k.append(None); self.v.append(None); self.seq_lens.append(0); self.seq_lens_dev.append(None)
+
+    def reserve(self, layer_idx: int, batch: int, kv_heads: int, rows: int, head_dim: int, dtype, device):
+        """Allocate (once) the layer buffer with room for ``rows`` compact rows + max_new_tokens."""
+        self._grow_lists(layer_idx)
+        cap = rows + self.max_new_tokens
+        cur = self.k[layer_idx]
+        if cur is None or cur.shape[0] != batch or cur.shape[1] != kv_heads or cur.shape[2] < cap or cur.dtype != dtype:
+            self.k[layer_idx] = torch.empty((batch, kv_heads, cap, head_dim), dtype=dtype, device=device)
+            self.v[layer_idx] = torch.empty((batch, kv_heads, cap, head_dim), dtype=dtype, device=device)
+            self.seq_lens_dev[layer_idx] = torch.zeros(1, dtype=torch.int32, device=device)
+        return self.k[layer_idx], self.v[layer_idx]
+
+    def set_length(self, layer_idx: int, n: int):
+        self.seq_lens[layer_idx] = int(n)
+        self.seq_lens_dev[layer_idx].fill_(int(n))
+
+    def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None
+               ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Prefill (rows > 1): store the given (already compacted) rows.  Decode (1 row): append in place.
+
+        Returns views of the valid rows, like ``DynamicCache.update``."""
+        b, h, rows, d = key_states.shape
+        self._grow_lists(layer_idx)
+        if rows > 1 or self.k[layer_idx] is None:
+            kbuf, vbuf = self.reserve(layer_idx, b, h, rows, d, key_states.dtype, key_states.device)
+            if key_states.data_ptr() != kbuf.data_ptr():      # the compress kernel may already have written in place
+                kbuf[:, :, :rows].copy_(key_states)
+                vbuf[:, :, :rows].copy_(value_states)
+            self.set_length(layer_idx, rows)
+            if layer_idx == 0:
+                self.true_length = max(self.true_length, rows)
+        else:
+            kbuf, vbuf = self.k[layer_idx], self.v[layer_idx]
+            n = self.seq_lens[layer_idx]
+            if n >= kbuf.shape[2]:
+                raise RuntimeError("CompactKVCache is full: raise max_new_tokens")
+            if key_states.is_cuda:
+                ops.cache_append(key_states, value_states, kbuf, vbuf, n)
+            else:                                             # CPU plumbing tests only (no kernels involved)
+                kbuf[:, :, n] = key_states[:, :, 0]
+                vbuf[:, :, n] = value_states[:, :, 0]
+            self.seq_lens[layer_idx] = n + 1
+            self.seq_lens_dev[layer_idx].add_(1)
+            if layer_idx == 0:
+                self.true_length += 1
+        n = self.seq_lens[layer_idx]
+        return self.k[layer_idx][:, :, :n], self.v[layer_idx][:, :, :n]
+
+    def buffers(self, layer_idx: int):
+        """(k_buffer, v_buffer, seq_len, seq_len_dev) for the decode-attention kernel."""
+        return self.k[layer_idx], self.v[layer_idx], self.seq_lens[layer_idx], self.seq_lens_dev[layer_idx]

@@ -48,21 +48,25 @@ class HeadShard:
         return head_range(num_heads, self.rank, self.world_size)
 
     # -- the exchange -----------------------------------------------------------------------------
-    def exchange_scores(self, score_local: torch.Tensor) -> torch.Tensor:
+    def exchange_scores(self, score_local: torch.Tensor, partial: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B, Hl, P] rank-local scores -> what the global top-k consumes.
 
-        gather: [B, Hl * N, P] in global head order;  reduce: [B, 1, P] all-reduced partial sums."""
+        gather: [B, Hl * N, P] in global head order;  reduce: [B, 1, P] all-reduced partial sums
+        (``partial`` = this rank's fixed-order head sum, computed on device when not given)."""
         n = self.world_size
         if n == 1:
             return score_local
         b, hl, p = score_local.shape
         if self.exchange == "gather":
-            gathered = torch.empty((n, b, hl, p), dtype=score_local.dtype, device=score_local.device)
-            dist.all_gather_into_tensor(gathered, score_local.contiguous(), group=self.group)
+            flat = torch.empty((n * b, hl, p), dtype=score_local.dtype, device=score_local.device)
+            dist.all_gather_into_tensor(flat, score_local.contiguous(), group=self.group)   # rank-major concat on dim 0
+            gathered = flat.view(n, b, hl, p)
             if b == 1:
                 return gathered.view(1, n * hl, p)
             return gathered.permute(1, 0, 2, 3).reshape(b, n * hl, p)
-        partial = local_importance(score_local)
+        if partial is None:
+            partial = local_importance(score_local)
+        partial = partial.clone()
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=self.group)
         return partial.view(b, 1, p)
 

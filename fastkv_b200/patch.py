@@ -1,0 +1,293 @@
+"""Monkeypatch entry points with the reference's names, re-hosted on the INSTALLED transformers.
+
+Mirrors ``baselines/monkeypatch.py``: ``replace_llama(method)`` :12, ``replace_mistral(method)`` :59,
+``set_model(model, args)`` :104, plus ``compress_fastkv`` / ``init_fastkv``
+(``baselines/fastkv/utils.py:25,137``).  The reference patches transformers 4.45 symbols
+(``LlamaFlashAttention2``, ``LLAMA_ATTENTION_CLASSES``) that no longer exist; here the three
+``forward`` methods of the current ``*Attention`` / ``*DecoderLayer`` / ``*Model`` classes are
+replaced and every attention module gets its ``kv_cluster``:
+
+* attention forward  — prefill: ``kv_cluster.update_kv`` compacts K/V into the cache while the layer
+  still attends over the FULL K/V; decode: append + attention over the compact cache
+  (baselines/fastkv/llama_model.py:136-145, :181-183; mistral_model.py:100-107)
+* decoder layer      — after the MLP residual of the TSP layer, propagate only the selected tokens'
+  hidden states and position ids (llama_model.py:252-259; mistral_model.py:217-224)
+* model forward      — swap in the new position ids / rotary embeddings after the TSP layer and
+  return only the last token's hidden state (llama_model.py:368-371, :392; mistral_model.py:328-351)
+
+Supported methods: ``fastkv``, ``snapkv`` (selection through the same kernels), ``fullkv``.
+The other baselines of the reference (h2o, streamingllm, pyramidinfer, gemfilter's two-pass driver)
+are outside the hot path and raise ``NotImplementedError``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .cache import CompactKVCache
+from .cluster import FastKVCluster, SnapKVCluster
+
+_ORIGINALS = {}
+
+
+# ---------------------------------------------------------------------------------------------
+# knob plumbing (same attribute / argument names as the reference)
+# ---------------------------------------------------------------------------------------------
+def init_fastkv(self):
+    """baselines/fastkv/utils.py:137-138."""
+    self.kv_cluster = FastKVCluster()
+
+
+def init_snapkv(self):
+    """baselines/snapkv/utils.py:105-126 (defaults written onto self.config when absent)."""
+    cfg = self.config
+    for name, default in (("window_size", 32), ("max_capacity_prompt", 4096), ("kernel_size", 5),
+                          ("pooling", "avgpool"), ("merge", None), ("retain_rate", 0.25), ("eviction_mode", "constant")):
+        if not hasattr(cfg, name):
+            setattr(cfg, name, default)
+    self.kv_cluster = SnapKVCluster(window_size=cfg.window_size, max_capacity_prompt=cfg.max_capacity_prompt,
+                                    kernel_size=cfg.kernel_size, pooling=cfg.pooling, merge=cfg.merge,
+                                    retain_rate=cfg.retain_rate, eviction_mode=cfg.eviction_mode)
+
+
+def compress_fastkv(model, args):
+    """baselines/fastkv/utils.py:25-46: write the knobs onto every layer's cluster."""
+    layers = len(model.model.layers)
+    for i in range(layers):
+        cl = model.model.layers[i].self_attn.kv_cluster
+        cl.window_size = args.window_size[i]
+        cl.kernel_size = args.kernel_size[i]
+        cl.pooling = args.pooling
+        cl.max_capacity_prompt = args.max_capacity_prompts
+        cl.tsp_length = args.tsp_len
+        cl.tsp_rate = args.tsp_rate
+        cl.eviction_mode = args.eviction_mode
+        cl.tsp_layer = (i == args.tsp_idx)
+        if i <= args.tsp_idx:
+            cl.retain_rate = args.retain_rate
+        else:
+            cl.retain_rate = args.retain_rate / args.tsp_rate
+
+
+def set_model(model, args):
+    """baselines/monkeypatch.py:104-147 (fastkv / snapkv / fullkv branches)."""
+    if args.max_capacity_prompts != -1:
+        max_capacity_prompts = args.max_capacity_prompts
+    else:
+        # the reference leaves this unbound (monkeypatch.py:105-106); fail loudly instead
+        raise ValueError("max_capacity_prompts == -1 is not supported")
+    if args.method == "fullkv":
+        return
+    if args.method not in ("fastkv", "snapkv"):
+        raise NotImplementedError(f"method {args.method!r} is outside the FastKV hot path")
+    window_size, kernel_size, pooling, retain_rate = args.window_size, args.kernel_size, args.pooling, args.retain_rate
+    layers = len(model.model.layers)
+    if not isinstance(window_size, list):
+        window_size = [window_size] * layers
+    if not isinstance(max_capacity_prompts, list):
+        max_capacity_prompts = [max_capacity_prompts] * layers
+    if not isinstance(kernel_size, list):
+        kernel_size = [kernel_size] * layers
+    if not isinstance(retain_rate, list):
+        retain_rate = [retain_rate] * layers
+    for i in range(layers):
+        cfg = model.model.layers[i].self_attn.config
+        cfg.window_size = window_size[i]
+        cfg.max_capacity_prompt = max_capacity_prompts[i]
+        cfg.kernel_size = kernel_size[i]
+        cfg.pooling = pooling
+        cfg.merge = getattr(args, "merge", None)
+        cfg.retain_rate = retain_rate[i]
+        cfg.eviction_mode = args.eviction_mode
+    if args.method == "fastkv":
+        args.window_size = window_size
+        args.kernel_size = kernel_size
+        for layer in model.model.layers:
+            if not isinstance(getattr(layer.self_attn, "kv_cluster", None), FastKVCluster):
+                init_fastkv(layer.self_attn)
+        compress_fastkv(model, args)
+    else:  # snapkv: per-layer clusters read their knobs from the layer config (snapkv/utils.py:105-126)
+        for i, layer in enumerate(model.model.layers):
+            init_snapkv(layer.self_attn)
+            layer.self_attn.kv_cluster.max_capacity_prompt = max_capacity_prompts[i]
+            layer.self_attn.kv_cluster.window_size = window_size[i]
+            layer.self_attn.kv_cluster.kernel_size = kernel_size[i]
+
+
+# ---------------------------------------------------------------------------------------------
+# patched forwards (shared by Llama and Mistral; `mod` is the transformers modeling module)
+# ---------------------------------------------------------------------------------------------
+def _make_forwards(mod, method, sliding_window_attr=False):
+    apply_rotary_pos_emb = mod.apply_rotary_pos_emb
+    eager_attention_forward = mod.eager_attention_forward
+    ALL_ATTENTION_FUNCTIONS = mod.ALL_ATTENTION_FUNCTIONS
+    BaseModelOutputWithPast = mod.BaseModelOutputWithPast
+
+    def attn_forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        input_shape = hidden_states.shape[:-1]
+        q_len = hidden_states.shape[1]
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
+
+        decode_native = False
+        if past_key_values is not None:
+            if q_len > 1:
+                # prefill: compact K/V go to the cache, the layer itself still attends over everything
+                if not hasattr(self, "kv_cluster"):
+                    init_fastkv(self) if method == "fastkv" else init_snapkv(self)
+                if method == "fastkv":
+                    k_c, v_c, self.tsp_idx = self.kv_cluster.update_kv(
+                        key_states, query_states, value_states, attention_mask, self.num_key_value_groups, self.layer_idx)
+                else:
+                    k_c, v_c = self.kv_cluster.update_kv(
+                        key_states, query_states, value_states, attention_mask, self.num_key_value_groups)
+                    self.tsp_idx = None
+                past_key_values.update(k_c, v_c, self.layer_idx)
+            else:
+                key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
+                self.tsp_idx = None
+                decode_native = (isinstance(past_key_values, CompactKVCache) and key_states.is_cuda
+                                 and key_states.shape[1] * self.num_key_value_groups == query_states.shape[1]
+                                 and self.head_dim in (64, 128))
+        if decode_native:
+            # K5: split-K decode attention straight over the pre-allocated compact cache
+            kbuf, vbuf, n, _ = past_key_values.buffers(self.layer_idx)
+            out = ops.decode_attn(query_states[:, :, 0, :], kbuf, vbuf, n, scale=self.scaling)     # [B,Hq,D]
+            attn_output = out.reshape(input_shape[0], 1, -1)
+            attn_weights = None
+        else:
+            if method == "snapkv" and key_states.shape[1] != query_states.shape[1] and q_len == 1:
+                pass                                  # GQA handled by the attention interface
+            attention_interface = ALL_ATTENTION_FUNCTIONS.get_interface(self.config._attn_implementation, eager_attention_forward)
+            extra = {}
+            if sliding_window_attr:
+                extra["sliding_window"] = getattr(self.config, "sliding_window", None)
+            attn_output, attn_weights = attention_interface(
+                self, query_states, key_states, value_states, attention_mask,
+                dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **extra, **kwargs)
+            attn_output = attn_output.reshape(*input_shape, -1).contiguous()
+        attn_output = self.o_proj(attn_output)
+        return attn_output, attn_weights
+
+    def decoder_forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_values=None,
+                        use_cache=False, position_embeddings=None, **kwargs):
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, _ = self.self_attn(
+            hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
+            past_key_values=past_key_values, use_cache=use_cache, position_embeddings=position_embeddings, **kwargs)
+        hidden_states = residual + hidden_states
+        residual = hidden_states
+        hidden_states = self.post_attention_layernorm(hidden_states)
+        hidden_states = self.mlp(hidden_states)
+        hidden_states = residual + hidden_states
+
+        # [FastKV] select important tokens and adjust position_ids at the TSP layer
+        tsp_idx = getattr(self.self_attn, "tsp_idx", None)
+        cluster = getattr(self.self_attn, "kv_cluster", None)
+        if cluster is not None and getattr(cluster, "tsp_layer", False) and tsp_idx is not None:
+            hidden_states, self.new_position_ids = ops.gather_rows(hidden_states, tsp_idx, position_ids)
+        else:
+            self.new_position_ids = None
+        return hidden_states
+
+    def model_forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None,
+                      inputs_embeds=None, use_cache=None, **kwargs):
+        if (input_ids is None) ^ (inputs_embeds is not None):
+            raise ValueError("You must specify exactly one of input_ids or inputs_embeds")
+        for drop in ("output_attentions", "output_hidden_states", "return_dict", "cache_position"):
+            kwargs.pop(drop, None)
+        if inputs_embeds is None:
+            inputs_embeds = self.embed_tokens(input_ids)
+        if use_cache is None:
+            use_cache = self.config.use_cache
+        if use_cache and past_key_values is None:
+            past_key_values = CompactKVCache(self.config, max_new_tokens=getattr(self.config, "fastkv_max_new_tokens", 256))
+        if position_ids is None:
+            past_seen = past_key_values.get_seq_length() if past_key_values is not None else 0
+            position_ids = (torch.arange(inputs_embeds.shape[1], device=inputs_embeds.device) + past_seen).unsqueeze(0)
+        q_len = inputs_embeds.shape[1]
+        if attention_mask is not None and attention_mask.dim() == 2 and not bool(attention_mask.all()):
+            # the reference's padded-batch path is broken (llama_model.py:57,77)
+            raise NotImplementedError("padded batches are not supported on the FastKV path")
+        # un-padded prompts: pure causal attention (prefill) / everything visible (decode)
+        causal_mask = None
+        hidden_states = inputs_embeds
+        position_embeddings = self.rotary_emb(hidden_states, position_ids=position_ids)
+        is_causal_kw = {} if q_len > 1 else {"is_causal": False}
+        for decoder_layer in self.layers[: self.config.num_hidden_layers]:
+            hidden_states = decoder_layer(
+                hidden_states, attention_mask=causal_mask, position_embeddings=position_embeddings,
+                position_ids=position_ids, past_key_values=past_key_values, use_cache=use_cache, **is_causal_kw, **kwargs)
+            new_position_ids = getattr(decoder_layer, "new_position_ids", None)
+            if new_position_ids is not None:          # [FastKV] later layers run on the TSP-selected tokens only
+                position_ids = new_position_ids
+                position_embeddings = self.rotary_emb(hidden_states, position_ids=position_ids)
+        hidden_states = self.norm(hidden_states)
+        hidden_states = hidden_states[:, -1:, :]      # [FastKV] only the last token feeds lm_head
+        return BaseModelOutputWithPast(last_hidden_state=hidden_states, past_key_values=past_key_values)
+
+    return attn_forward, decoder_forward, model_forward
+
+
+def _patch(mod, prefix, method, sliding):
+    attn_cls = getattr(mod, prefix + "Attention")
+    layer_cls = getattr(mod, prefix + "DecoderLayer")
+    model_cls = getattr(mod, prefix + "Model")
+    key = prefix
+    if key not in _ORIGINALS:
+        _ORIGINALS[key] = (attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__)
+    o_attn, o_layer, o_model, o_init = _ORIGINALS[key]
+    if method == "fullkv":
+        attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__ = o_attn, o_layer, o_model, o_init
+        return
+    if method not in ("fastkv", "snapkv"):
+        raise NotImplementedError(f"No method found for {method}: only fastkv / snapkv / fullkv are on the hot path")
+    attn_f, layer_f, model_f = _make_forwards(mod, method, sliding_window_attr=sliding)
+
+    def patched_init(self, *args, **kwargs):
+        o_init(self, *args, **kwargs)
+        if method == "fastkv":
+            init_fastkv(self)                          # LlamaFastKVAttention.__init__ (llama_model.py:89-91)
+        self.tsp_idx = None
+
+    attn_cls.__init__ = patched_init
+    attn_cls.forward = attn_f
+    layer_cls.forward = layer_f
+    model_cls.forward = model_f
+
+
+def replace_llama(method):
+    """baselines/monkeypatch.py:12-56."""
+    from transformers.models.llama import modeling_llama as mod
+    _patch(mod, "Llama", method, sliding=False)
+
+
+def replace_mistral(method):
+    """baselines/monkeypatch.py:59-102."""
+    from transformers.models.mistral import modeling_mistral as mod
+    _patch(mod, "Mistral", method, sliding=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's hand-rolled greedy loop (benchmark/e2e.py:162-183), used by bench / tests
+# ---------------------------------------------------------------------------------------------
+@torch.no_grad()
+def greedy_generate(model, input_ids, genlen, attention_mask=None, max_new_tokens=None):
+    """Prefill + (genlen - 1) decode steps; returns (token ids [B, genlen], cache)."""
+    model.config.fastkv_max_new_tokens = max_new_tokens or genlen
+    if hasattr(model, "model"):
+        model.model.config.fastkv_max_new_tokens = model.config.fastkv_max_new_tokens
+    out = model(input_ids, attention_mask=attention_mask, use_cache=True)
+    cache = out.past_key_values
+    tok = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
+    toks = [tok]
+    for _ in range(genlen - 1):
+        out = model(input_ids=tok, past_key_values=cache, use_cache=True)
+        tok = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
+        toks.append(tok)
+    return torch.cat(toks, dim=1), cache

@@ -1,0 +1,102 @@
+"""GPU tests of the patched model forwards against the CPU glue oracle."""
+import types
+
+import pytest
+import torch
+
+from oracle import fastkv_oracle as O
+from oracle import glue_oracle as G
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model(dtype, layers=3, seed=0):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=layers, num_attention_heads=8,
+                      num_key_value_heads=2, head_dim=64, vocab_size=211, max_position_embeddings=4096,
+                      attn_implementation="sdpa")
+    torch.manual_seed(seed)
+    return LlamaForCausalLM(cfg).eval().to(dtype)
+
+
+def _args(**kw):
+    base = dict(method="fastkv", max_capacity_prompts=128, window_size=8, kernel_size=7, pooling="avgpool",
+                retain_rate=0.1, eviction_mode="constant", tsp_len=256, tsp_rate=0.2, tsp_idx=1, merge=None)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.fixture
+def patched():
+    from fastkv_b200 import patch
+    patch.replace_llama("fastkv")
+    yield patch
+    patch.replace_llama("fullkv")
+
+
+def test_fp32_prefill_matches_glue_oracle(patched):
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    model = _model(torch.float32)
+    ids = torch.randint(0, 211, (2, 600), generator=torch.Generator().manual_seed(3))
+    args = _args()
+    knobs = [dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=(i == 1), tsp_length=256)
+             for i in range(3)]
+    patched.replace_llama("fullkv")
+    ref_hidden, ref_caches, traces = G.fastkv_prefill(model, ids, knobs, apply_rotary_pos_emb)
+    patched.replace_llama("fastkv")
+    gm = _model(torch.float32).to(DEV)
+    patched.set_model(gm, args)
+    for layer in gm.model.layers:
+        layer.self_attn.kv_cluster.keep_aux = True
+    with torch.no_grad():
+        out = gm.model(ids.to(DEV), use_cache=True)
+    torch.cuda.synchronize()
+    cache = out.past_key_values
+    # TSP layer: same token set (near-tie aware against the oracle's own importance)
+    tsp = gm.model.layers[1].self_attn.tsp_idx
+    assert tsp is not None and tsp.shape == (2, 256)
+    for b in range(2):
+        assert O.near_tie_set_mismatch(traces[1].importance[b], ref_caches[1][2][b, :-8], tsp[b, :-8].cpu()) == 0
+    # later layers ran on T tokens: q_len (256) >= C (128) -> compacted again to C rows
+    for i in range(3):
+        k_ref, v_ref, _ = ref_caches[i]
+        kbuf, vbuf, n, _ = cache.buffers(i)
+        assert n == k_ref.shape[2] == 128
+        idx = gm.model.layers[i].self_attn.kv_cluster.last_aux["idx"].cpu()
+        if torch.equal(idx, traces[i].idx):
+            assert torch.allclose(kbuf[:, :, :n].cpu(), k_ref, atol=2e-4, rtol=1e-4)
+            assert torch.allclose(vbuf[:, :, :n].cpu(), v_ref, atol=2e-4, rtol=1e-4)
+    if torch.equal(tsp.cpu(), ref_caches[1][2]):
+        assert torch.allclose(out.last_hidden_state.cpu(), ref_hidden, atol=2e-3, rtol=1e-3)
+    assert out.last_hidden_state.shape == (2, 1, 512)
+
+
+def test_bf16_prefill_and_native_decode(patched):
+    """Decode over the compact cache with the K5 kernel agrees with HF attention over the same cache."""
+    from fastkv_b200 import ops
+    model = _model(torch.bfloat16).to(DEV)
+    patched.set_model(model, _args())
+    ids = torch.randint(0, 211, (1, 1024), generator=torch.Generator().manual_seed(4)).to(DEV)
+    toks, cache = patched.greedy_generate(model, ids, 6)
+    assert toks.shape == (1, 6)
+    assert cache.get_seq_length(0) == 128 + 5 and cache.get_seq_length(2) == 128 + 5
+    # re-run the last decode step's attention of layer 0 with torch on the cached rows
+    kbuf, vbuf, n, ndev = cache.buffers(0)
+    assert int(ndev.item()) == n
+    q = torch.randn(1, 8, 64, device=DEV, dtype=torch.bfloat16)
+    got = ops.decode_attn(q, kbuf, vbuf, n)
+    exp = O.decode_attention(q.cpu(), kbuf.cpu(), vbuf.cpu(), n)
+    assert torch.allclose(got.cpu().float(), exp, atol=2e-2, rtol=2e-2)
+
+
+def test_snapkv_method_through_the_same_kernels(patched):
+    patched.replace_llama("snapkv")
+    model = _model(torch.bfloat16, layers=2).to(DEV)
+    patched.set_model(model, _args(method="snapkv", window_size=16, kernel_size=5, max_capacity_prompts=96))
+    ids = torch.randint(0, 211, (1, 512), generator=torch.Generator().manual_seed(5)).to(DEV)
+    with torch.no_grad():
+        out = model(ids, use_cache=True)
+    cache = out.past_key_values
+    assert cache.get_seq_length(0) == 96 and cache.k[0].shape[1] == 8      # one cache head per query head
+    assert torch.isfinite(out.logits).all()

@@ -1,0 +1,99 @@
+"""CPU tests of the monkeypatch plumbing (no kernels run: prompts shorter than the KV budget take
+the reference's early-return path, baselines/fastkv/utils.py:89-91)."""
+import types
+
+import pytest
+import torch
+
+
+def _tiny_llama(layers=2):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=layers, num_attention_heads=2,
+                      num_key_value_heads=1, head_dim=64, vocab_size=97, max_position_embeddings=512,
+                      attn_implementation="sdpa")
+    torch.manual_seed(0)
+    return LlamaForCausalLM(cfg).eval()
+
+
+def _args(**kw):
+    base = dict(method="fastkv", max_capacity_prompts=64, window_size=8, kernel_size=7, pooling="avgpool",
+                retain_rate=0.1, eviction_mode="constant", tsp_len=32, tsp_rate=0.2, tsp_idx=1, merge=None)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+@pytest.fixture
+def patched():
+    from fastkv_b200 import patch
+    patch.replace_llama("fastkv")
+    yield patch
+    patch.replace_llama("fullkv")
+
+
+def test_set_model_writes_the_reference_knobs(patched):
+    model = _tiny_llama(3)
+    args = _args(tsp_idx=1, eviction_mode="proportional")
+    patched.set_model(model, args)
+    cl = [l.self_attn.kv_cluster for l in model.model.layers]
+    assert [c.tsp_layer for c in cl] == [False, True, False]                 # fastkv/utils.py:38-41
+    assert cl[0].retain_rate == 0.1 and cl[2].retain_rate == pytest.approx(0.1 / 0.2)   # :43-46
+    assert all(c.window_size == 8 and c.kernel_size == 7 and c.max_capacity_prompt == 64 for c in cl)
+    assert all(c.tsp_length == 32 and c.pooling == "avgpool" and c.eviction_mode == "proportional" for c in cl)
+    assert model.model.layers[0].self_attn.config.max_capacity_prompt == 64  # monkeypatch.py:132-139
+    assert isinstance(args.window_size, list)                                # :145-146
+
+
+def test_short_prompt_matches_stock_model_and_decodes(patched):
+    from fastkv_b200.cache import CompactKVCache
+    model = _tiny_llama()
+    ids = torch.randint(0, 97, (1, 20), generator=torch.Generator().manual_seed(1))
+    patched.replace_llama("fullkv")
+    with torch.no_grad():
+        ref = model(ids, use_cache=True)
+        ref_next = ref.logits[:, -1].argmax(-1, keepdim=True)
+        ref2 = model(ref_next, past_key_values=ref.past_key_values, use_cache=True).logits[:, -1]
+    patched.replace_llama("fastkv")
+    patched.set_model(model, _args())
+    with torch.no_grad():
+        out = model(ids, use_cache=True)
+    assert out.logits.shape[1] == 1                                          # last-token cut (llama_model.py:392)
+    assert torch.allclose(out.logits[:, -1], ref.logits[:, -1], atol=1e-5)
+    cache = out.past_key_values
+    assert isinstance(cache, CompactKVCache) and cache.get_seq_length() == 20
+    with torch.no_grad():
+        out2 = model(out.logits[:, -1].argmax(-1, keepdim=True), past_key_values=cache, use_cache=True)
+    assert cache.get_seq_length() == 21
+    assert torch.allclose(out2.logits[:, -1], ref2, atol=1e-4)
+    toks, _ = patched.greedy_generate(model, ids, 4)
+    assert toks.shape == (1, 4) and toks[0, 0] == ref_next[0, 0]
+
+
+def test_unsupported_methods_fail_loudly(patched):
+    with pytest.raises(NotImplementedError):
+        patched.replace_llama("h2o")
+    with pytest.raises(NotImplementedError):
+        patched.set_model(_tiny_llama(), _args(method="streamingllm"))
+
+
+def test_mistral_patch_installs(patched):
+    from transformers.models.mistral import modeling_mistral as mm
+    orig = mm.MistralModel.forward
+    patched.replace_mistral("fastkv")
+    assert mm.MistralModel.forward is not orig
+    patched.replace_mistral("fullkv")
+    assert mm.MistralModel.forward is orig
+
+
+def test_compact_cache_update_contract():
+    from fastkv_b200.cache import CompactKVCache
+    c = CompactKVCache(max_new_tokens=4)
+    k, v = torch.randn(2, 2, 10, 64), torch.randn(2, 2, 10, 64)
+    ko, vo = c.update(k, v, 0)
+    assert ko.shape == (2, 2, 10, 64) and torch.equal(ko, k) and c.get_seq_length() == 10
+    k1, v1 = torch.randn(2, 2, 1, 64), torch.randn(2, 2, 1, 64)
+    ko, vo = c.update(k1, v1, 0)
+    assert ko.shape[2] == 11 and torch.equal(ko[:, :, 10], k1[:, :, 0]) and torch.equal(vo[:, :, :10], v)
+    for _ in range(3):
+        c.update(k1, v1, 0)
+    with pytest.raises(RuntimeError):
+        c.update(k1, v1, 0)
