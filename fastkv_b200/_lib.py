@@ -110,7 +110,7 @@ class CompressParams(C.Structure):
 
 
 EXPORTS = [
-    "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
+    "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
     "fkv_score_impl_name", "fkv_launch_count",
     "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append", "fkv_compress",
 ]
@@ -138,6 +138,8 @@ def load():
         lib.fkv_strerror.argtypes = [C.c_int]
         lib.fkv_workspace_bytes.restype = C.c_size_t
         lib.fkv_workspace_bytes.argtypes = [C.c_int32] * 8
+        lib.fkv_workspace_init.restype = C.c_int
+        lib.fkv_workspace_init.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
         lib.fkv_topk_workspace_bytes.restype = C.c_size_t
         lib.fkv_topk_workspace_bytes.argtypes = [C.c_int32] * 3
         lib.fkv_decode_workspace_bytes.restype = C.c_size_t
@@ -211,5 +213,6 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        check(load().fkv_workspace_init(buf.data_ptr(), buf.numel(), torch.cuda.current_stream(device).cuda_stream))
         _workspaces[key] = buf
     return buf

@@ -116,6 +116,12 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
   return b + 4096;
 }
 
+int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+  if (!workspace || workspace_bytes < 256) return FKV_EWORKSPACE;
+  FKV_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
+  return FKV_OK;
+}
+
 size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k) { return topk_workspace_bytes(rows, n, k); }
 
 size_t fkv_decode_workspace_bytes(int32_t B, int32_t Hq, int32_t D, int32_t max_seq_len) {

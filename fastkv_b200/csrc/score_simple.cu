@@ -264,7 +264,7 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
     FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set = true;
   }
-  char* ws = reinterpret_cast<char*>(p.workspace);
+  char* ws = reinterpret_cast<char*>(p.workspace) + 256;   // the first 256 bytes hold the tensor path's barrier counters
 
   if (p.mode == FKV_MODE_GEMFILTER) {
     const int qh0 = p.qh0, qh1 = (p.qh1 > p.qh0) ? p.qh1 : p.Hq;
@@ -314,14 +314,14 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
 // Scratch for the simple path (also an upper bound for the tensor path, which needs less).
 size_t score_workspace_bytes(int mode, int B, int Hq, int Hkv, int L, int W) {
   const int n_tiles = ceil_div(L, kTileKeys);
-  if (mode == FKV_MODE_GEMFILTER) return align_up((size_t)B * Hq * L * sizeof(float), 256);
+  if (mode == FKV_MODE_GEMFILTER) return 256 + align_up((size_t)B * Hq * L * sizeof(float), 256);
   const int Hsel = (mode == FKV_MODE_FASTKV) ? Hkv : Hq;
   const int G = (mode == FKV_MODE_FASTKV) ? Hq / Hkv : 1;
   size_t b = 0;
   b = align_up(b + (size_t)B * Hsel * n_tiles * G * W * sizeof(float2), 256);
   b = align_up(b + (size_t)B * Hsel * G * W * sizeof(float2), 256);
   b = align_up(b + (size_t)B * Hsel * G * (size_t)L * sizeof(float), 256);
-  return b + 1024;
+  return b + 1024 + 256;
 }
 
 int launch_score_simple(const fkv_score_params& p, cudaStream_t s) {

@@ -27,8 +27,10 @@ namespace fkv {
 namespace {
 
 constexpr int kTile = 128;
-constexpr int kTcThreads = 320;
-constexpr int kEpiThreads = 256;
+constexpr int kNumWG = 3;                  // epilogue warpgroups (tiles are dealt round-robin to them)
+constexpr int kEpiThreads = 128 * kNumWG;
+constexpr int kEpiWarps = 4 * kNumWG;
+constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kMaxLocalPairs = 8;
 constexpr int kMaxStages = 6;
 constexpr float kLazyTau = 6.0f;          // log2 units of headroom before a running max is raised
@@ -36,12 +38,12 @@ constexpr float kEmptyMax = -1.0e30f;     // "no key seen yet" (finite, so exp2(
 
 struct TcArgs {
   int B, L, P, D, nkv, kv0, n_tiles, S, half, ks, pooling, group_sum, is_f16;
-  int U, maxlp, nst;
+  int U, maxlp, nst, maxc;
   int kpos_l, kpos_h, kpos_b, qpos_l, qpos_h, qpos_b;   // coordinate slots of the stride-sorted TMA dims
   int q_heads_per_kv;                                   // model G (query head = kvh * G + g)
   float c;                                              // softmax scale * log2(e)
   float2* part;                                         // [grid][maxlp][N] pass-1 partial (max, sum)
-  unsigned int* sync_counter;                           // zeroed before launch
+  unsigned int* sync_counter;                           // [0] arrivals, [1] departures; zero on entry, left zero on exit
   unsigned long long* trace;                            // optional [grid][16] globaltimer stamps (FKV_TC_TRACE=1)
   float* score; int64_t score_sb, score_sh; int out_h0;
 };
@@ -170,8 +172,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);   // full[6] empty[6] qfull[2] qempty[2] tfull[32] tempty[32] rdone[32]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 112);
   float2* stage = reinterpret_cast<float2*>(tmem_slot + 4);             // [8][N]
-  float2* colstat = stage + 8 * N;                                      // [maxlp][N]
-  float* vbuf = reinterpret_cast<float*>(colstat + kMaxLocalPairs * N); // [2 wg][2 buf][G][128]
+  float2* colstat = stage + kEpiWarps * N;                              // [maxlp][N]
+  float* vbuf = reinterpret_cast<float*>(colstat + kMaxLocalPairs * N); // [wg][2 buf][G][128]
+  int* ncontrib = reinterpret_cast<int*>(vbuf + kNumWG * 2 * G * kTile);     // [maxlp] CTAs contributing to each local pair
 
   auto bar_full = [&](int s) { return smem_u32(bars + s); };
   auto bar_empty = [&](int s) { return smem_u32(bars + 6 + s); };
@@ -195,10 +198,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   // fills of block b during pass 1
   auto fills_pass1 = [&](int b) { return (T - 1 - b) / NB + 1; };
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kMaxStages; ++s) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(bar_qfull(s), 1); mbar_init(bar_qempty(s), 1); }
-    for (int s = 0; s < NB; ++s) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128); mbar_init(bar_rdone(s), 128); }
+  if (warp == 0) {                                  // 112 barriers, a few per lane
+    for (int s = lane; s < kMaxStages; s += 32) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
+    if (lane < 2) { mbar_init(bar_qfull(lane), 1); mbar_init(bar_qempty(lane), 1); }
+    for (int s = lane; s < NB; s += 32) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128); mbar_init(bar_rdone(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -237,21 +240,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
           const int u = u0 + T - NB - 1;
           pair = u / a.n_tiles; t = u - pair * a.n_tiles;
         }
-        if (pair != cur_pair) {                      // new (b, h): stage its N query rows (B operand)
+        const bool new_pair = (pair != cur_pair);
+        int pb = 0, pkvh = 0;
+        if (new_pair) {
           cur_pair = pair; ++qu;
-          const int b = pair / a.nkv, kvh = a.kv0 + pair - b * a.nkv;
-          hb1 = kvh * kh1 + b * kb1; hb2 = kvh * kh2 + b * kb2; hb3 = kvh * kh3 + b * kb3;
-          const int qb = qu & 1;
-          if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
-          mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
-          const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
-          for (int slab = 0; slab < slabs; ++slab)
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int hq = kvh * a.q_heads_per_kv + g;
-              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
-                          a.P * ql1 + hq * qh1 + b * qb1, a.P * ql2 + hq * qh2 + b * qb2, a.P * ql3 + hq * qh3 + b * qb3);
-            }
+          pb = pair / a.nkv; pkvh = a.kv0 + pair - pb * a.nkv;
+          hb1 = pkvh * kh1 + pb * kb1; hb2 = pkvh * kh2 + pb * kb2; hb3 = pkvh * kh3 + pb * kb3;
         }
         if (m >= a.nst) mbar_wait(bar_empty(slot), ephase);
         FKV_TRACE2(0, m);
@@ -261,6 +255,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         const int c1 = row0 * kl1 + hb1, c2 = row0 * kl2 + hb2, c3 = row0 * kl3 + hb3;
         tma_load_4d(kdst, &tm_k, bar_full(slot), 0, c1, c2, c3);
         if (slabs == 2) tma_load_4d(kdst + kTile * 128, &tm_k, bar_full(slot), 64, c1, c2, c3);
+        if (new_pair) {                              // new (b, h): stage its N query rows (B operand) after the K tile
+          const int qb = qu & 1;
+          if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
+          mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
+          const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
+          for (int slab = 0; slab < slabs; ++slab)
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const int hq = pkvh * a.q_heads_per_kv + g;
+              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
+                          a.P * ql1 + hq * qh1 + pb * qb1, a.P * ql2 + hq * qh2 + pb * qb2, a.P * ql3 + hq * qh3 + pb * qb3);
+            }
+        }
         if (m == T - 1) FKV_TRACE(10);
         if (++slot == a.nst) { slot = 0; ephase ^= 1; }
         if (m < T) { if (++t == a.n_tiles) { t = 0; ++pair; } }
@@ -339,7 +346,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // ===================================== epilogue =========================================
     const int et = threadIdx.x - 64;                 // 0..255
     const int ew = et >> 5;                          // epilogue warp 0..7
-    const int wg = ew >> 2;                          // warpgroup 0/1: alternate tiles
+    const int wg = ew >> 2;                          // warpgroup: tiles are dealt round-robin
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;             // tile row == TMEM lane
     const uint32_t my_tmem = tmem_base + ((uint32_t)(quarter * 32) << 16);
@@ -352,18 +359,31 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     int flushed = 0;                                 // local pairs already flushed by this warpgroup
     auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
       for (; flushed < lp_end; ++flushed) {
+        // Column sums across the warp by a halving butterfly: after the exchange with lane^16 a lane
+        // keeps the half of the columns selected by its bit 4, then bit 3, ... so lane l ends up with
+        // the total (and the reference max) of column l (N/32 groups of 32 columns): 31 shuffles
+        // instead of 160, and little straight-line code (cold instruction fetch dominates here).
 #pragma unroll
-        for (int n0 = 0; n0 < N; n0 += 8) {          // 8 independent shuffle chains at a time
-          float t8[8];
+        for (int g0 = 0; g0 < N; g0 += 32) {
+          constexpr int CW = N < 32 ? N : 32;         // columns in this group
+          float tz[CW], tm[CW];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) t8[i] = z[n0 + i];
+          for (int i = 0; i < CW; ++i) { tz[i] = z[g0 + i]; tm[i] = mn[g0 + i]; }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
+          for (int h = CW / 2; h >= 1; h >>= 1) {
+            const bool up = (lane & h) != 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) t8[i] += __shfl_xor_sync(0xffffffffu, t8[i], o);
+            for (int i = 0; i < h; ++i) {
+              const float keep = up ? tz[i + h] : tz[i];
+              const float send = up ? tz[i] : tz[i + h];
+              tz[i] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+              tm[i] = up ? tm[i + h] : tm[i];
+            }
+          }
+          // lanes >= CW (N < 32) hold partial duplicates: finish their reduction over the unused lane bits
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (lane == i) stage[ew * N + n0 + i] = make_float2(mn[n0 + i], t8[i]);
+          for (int o = 16; o >= CW; o >>= 1) tz[0] += __shfl_xor_sync(0xffffffffu, tz[0], o);
+          if (lane < CW) stage[ew * N + g0 + lane] = make_float2(tm[0], tz[0]);
         }
 #pragma unroll
         for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
@@ -373,14 +393,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         if (et < N) {
           float M = kEmptyMax;
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) M = fmaxf(M, stage[w8 * N + et].x);
+          for (int w8 = 0; w8 < kEpiWarps; ++w8) M = fmaxf(M, stage[w8 * N + et].x);
           float Z = 0.f;
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) {
+          for (int w8 = 0; w8 < kEpiWarps; ++w8) {
             const float2 v = stage[w8 * N + et];
             Z += v.y * ex2(v.x - M);
           }
-          a.part[((size_t)cta * a.maxlp + flushed) * N + et] = make_float2(M, Z);
+          const int pr = pair0 + flushed;
+          const int krank = cta - cta_of_unit((long long)pr * a.n_tiles, a.U, grid);
+          a.part[((size_t)pr * a.maxc + krank) * N + et] = make_float2(M, Z);
         }
         named_bar(2, kEpiThreads);
       }
@@ -389,7 +411,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // ---------------- pass 1: per-row softmax statistics over owned keys ----------------------
     int pair, t;
     { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
-    for (int j = wg; j < T; j += 2) {
+    for (int j = wg; j < T; j += kNumWG) {
       const int blk = j & (NB - 1);
       flush_upto(pair - pair0);
       mbar_wait(bar_tfull(blk), (j / NB) & 1);
@@ -437,7 +459,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
 #pragma unroll
         for (int n = 0; n < N; ++n) z[n] += ex2(fmaf(s[n], a.c, -mn[n]));
       }
-      t += 2;
+      t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
     if (et == 0) FKV_TRACE(3);
@@ -445,13 +467,18 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     if (et == 0) FKV_TRACE(4);
 
     // ---------------- grid barrier: every CTA's partials are visible ---------------------------
-    __threadfence();
+    // contributors of each local pair (needs no remote data: computed while others still arrive)
+    if (et < nlp) {
+      const long long ub = (long long)(pair0 + et) * a.n_tiles;
+      ncontrib[et] = cta_of_unit(ub + a.n_tiles - 1, a.U, grid) - cta_of_unit(ub, a.U, grid) + 1;
+    }
     tc_fence_before();
     if (et == 0) FKV_TRACE(13);
-    named_bar(2, kEpiThreads);
+    named_bar(2, kEpiThreads);                       // every partial of this CTA is ordered before ...
     if (et == 0) {
       FKV_TRACE(14);
-      atomicAdd(a.sync_counter, 1u);
+      // ... this release-arrive (cumulative at gpu scope); the counter is self-cleaning, see kernel end
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.sync_counter) : "memory");
       unsigned int seen;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sync_counter) : "memory");
@@ -462,24 +489,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     if (et == 0) FKV_TRACE(5);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
+    named_bar(2, kEpiThreads);
     // 8 lanes per row; every lane first issues all of its (up to 4) partial loads, then merges.
     for (int idx = et; idx < nlp * N * 8; idx += kEpiThreads) {
       const int sub = idx & 7, n = (idx >> 3) % N, lp = (idx >> 3) / N;
-      const int pair = pair0 + lp;
-      const long long ub = (long long)pair * a.n_tiles;
-      const long long ue = ub + a.n_tiles - 1;
-      const int c_lo = cta_of_unit(ub, a.U, grid), c_hi = cta_of_unit(ue, a.U, grid);
+      const int cnt = ncontrib[lp];
+      const float2* src = a.part + ((size_t)(pair0 + lp) * a.maxc) * N + n;
       float M = kEmptyMax, Z = 0.f;
-      for (int c0 = c_lo + sub; c0 <= c_hi; c0 += 32) {
+      for (int c0 = sub; c0 < cnt; c0 += 32) {
         float2 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int c = c0 + 8 * i;
-          v[i] = make_float2(kEmptyMax, 0.f);
-          if (c <= c_hi) {
-            const int lpc = pair - unit_begin(c, a.U, grid) / a.n_tiles;
-            v[i] = __ldcg(a.part + ((size_t)c * a.maxlp + lpc) * N + n);
-          }
+          v[i] = (c < cnt) ? __ldcg(src + (size_t)c * N) : make_float2(kEmptyMax, 0.f);
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -506,7 +528,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     const float inv_ks = 1.0f / (float)a.ks;
     int cur_lp = -1, b = 0, kvl = 0;
     { const int u = u0 + T - 1 - wg; pair = u >= 0 ? u / a.n_tiles : 0; t = u - pair * a.n_tiles; }
-    for (int j2 = wg; j2 < T; j2 += 2) {
+    for (int j2 = wg; j2 < T; j2 += kNumWG) {
       const int lt = T - 1 - j2;
       const int lp = pair - pair0;
       const int blk = lt & (NB - 1);
@@ -521,16 +543,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         mbar_wait(bar_tfull(blk), fill & 1);
       }
       tc_fence_after();
-      if (et == 0) FKV_TRACE2(4, j2 >> 1);
+      if (et == 0) FKV_TRACE2(4, j2 / kNumWG);
       float s[N];
       tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
-      if (et == 0) FKV_TRACE2(5, j2 >> 1);
+      if (et == 0) FKV_TRACE2(5, j2 / kNumWG);
       tc_fence_before();
       mbar_arrive(j2 >= NB ? bar_tempty(blk) : bar_rdone(blk));
       const int key = t * a.S - a.half + row;
       const bool in_prefix = (key >= 0) && (key < a.P);
-      float* vb = vbuf + ((wg * 2 + ((j2 >> 1) & 1)) * G) * kTile;
+      float* vb = vbuf + ((wg * 2 + ((j2 / kNumWG) & 1)) * G) * kTile;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float vote = 0.f;
@@ -539,9 +561,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
           vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mn[g * W + r])), z[g * W + r], vote);
         vb[g * kTile + row] = in_prefix ? vote : pad;
       }
-      if (et == 0) FKV_TRACE2(6, j2 >> 1);
+      if (et == 0) FKV_TRACE2(6, j2 / kNumWG);
       named_bar(3 + wg, 128);
-      if (et == 0) FKV_TRACE2(7, j2 >> 1);
+      if (et == 0) FKV_TRACE2(7, j2 / kNumWG);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
       if (own) {
         float acc = 0.f;
@@ -570,13 +592,19 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         }
         if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
       }
-      if (et == 0) FKV_TRACE2(8, j2 >> 1);
-      t -= 2;
+      if (et == 0) FKV_TRACE2(8, j2 / kNumWG);
+      t -= kNumWG;
       while (t < 0) { t += a.n_tiles; --pair; }
     }
   }
 
-  if (threadIdx.x == 64) FKV_TRACE(7);
+  if (threadIdx.x == 64) {
+    FKV_TRACE(7);
+    // departure count: the last CTA out resets both counters, so the next launch on this stream
+    // finds them zero again (no memset node in front of every call)
+    const unsigned int prev = atomicAdd(a.sync_counter + 1, 1u);
+    if (prev == (unsigned)grid - 1) { a.sync_counter[0] = 0u; a.sync_counter[1] = 0u; __threadfence(); }
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 64) FKV_TRACE(8);
@@ -646,7 +674,7 @@ int make_map(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int 
 }
 
 struct Plan {
-  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst;
+  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst, maxc;
   size_t smem, part_bytes;
   bool ok;
 };
@@ -679,14 +707,16 @@ Plan make_plan(const fkv_score_params& p) {
   const int NMMA = pl.N < 16 ? 16 : pl.N;
   const size_t tile_bytes = (size_t)kTile * p.D * 2;
   const size_t q_bytes = ((size_t)NMMA * p.D * 2 + 1023) & ~(size_t)1023;
-  const size_t misc = 112 * 8 + 16 + (size_t)8 * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)2 * 2 * pl.G * kTile * 4;
+  const size_t misc = 112 * 8 + 16 + (size_t)kEpiWarps * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)kNumWG * 2 * pl.G * kTile * 4 + kMaxLocalPairs * 4;
   const size_t budget = 227 * 1024 - 1024 - 2 * q_bytes - misc - 256;
   int nst = (int)(budget / tile_bytes);
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) return pl;
   pl.nst = nst;
   pl.smem = 1024 + nst * tile_bytes + 2 * q_bytes + misc + 256;
-  pl.part_bytes = align_up((size_t)pl.grid * pl.maxlp * pl.N * sizeof(float2), 256);
+  const int per_min = pl.U / pl.grid;               // every CTA owns at least this many units
+  pl.maxc = ceil_div(pl.n_tiles, per_min > 0 ? per_min : 1) + 2;
+  pl.part_bytes = align_up((size_t)p.B * pl.nkv * pl.maxc * pl.N * sizeof(float2), 256);
   pl.ok = true;
   return pl;
 }
@@ -725,7 +755,7 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   a.B = p.B; a.L = p.L; a.P = p.L - p.window_size; a.D = p.D;
   a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
   a.pooling = p.pooling; a.group_sum = (p.mode == FKV_MODE_FASTKV); a.is_f16 = (p.dtype == FKV_F16);
-  a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.q_heads_per_kv = pl.G;
+  a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.maxc = pl.maxc; a.q_heads_per_kv = pl.G;
   a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
   char* ws = reinterpret_cast<char*>(p.workspace);
   a.sync_counter = reinterpret_cast<unsigned int*>(ws);
@@ -736,7 +766,6 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   int rc;
   if ((rc = make_map(&mk, p.k, p.dtype, p.B, p.Hkv, p.L, p.D, kTile, &a.kpos_l, &a.kpos_h, &a.kpos_b)) != FKV_OK) return rc;
   if ((rc = make_map(&mq, p.q, p.dtype, p.B, p.Hq, p.L, p.D, pl.W, &a.qpos_l, &a.qpos_h, &a.qpos_b)) != FKV_OK) return rc;
-  FKV_CUDA_TRY(cudaMemsetAsync(a.sync_counter, 0, 4, s));
   static const bool trace_on = getenv("FKV_TC_TRACE") != nullptr;
   static unsigned long long* trace_buf = nullptr;
   if (trace_on) {
