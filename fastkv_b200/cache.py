@@ -32,6 +32,7 @@ class CompactKVCache:
         self.seq_lens: List[int] = []                 # host mirror of the per-layer length
         self.seq_lens_dev: List[Optional[torch.Tensor]] = []   # int32 [1] on device (CUDA-graph friendly)
         self.true_length = 0                           # prompt length + generated tokens (not compacted)
+        self.device_lengths = False                    # True: decode steps advance the device-side lengths only
 
     # -- HF Cache surface -----------------------------------------------------------------------
     def __len__(self):
@@ -96,6 +97,12 @@ class CompactKVCache:
                 self.true_length += 1
         n = self.seq_lens[layer_idx]
         return self.k[layer_idx][:, :, :n], self.v[layer_idx][:, :, :n]
+
+    def sync_lengths(self):
+        """Refresh the host mirrors from the device-side lengths (after graph-replayed decode steps)."""
+        for i, d in enumerate(self.seq_lens_dev):
+            if d is not None:
+                self.seq_lens[i] = int(d.item())
 
     def buffers(self, layer_idx: int):
         """(k_buffer, v_buffer, seq_len, seq_len_dev) for the decode-attention kernel."""

@@ -148,11 +148,19 @@ def _make_forwards(mod, method, sliding_window_attr=False):
                     self.tsp_idx = None
                 past_key_values.update(k_c, v_c, self.layer_idx)
             else:
-                key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
                 self.tsp_idx = None
-                decode_native = (isinstance(past_key_values, CompactKVCache) and key_states.is_cuda
-                                 and key_states.shape[1] * self.num_key_value_groups == query_states.shape[1]
-                                 and self.head_dim in (64, 128))
+                native_ok = (isinstance(past_key_values, CompactKVCache) and key_states.is_cuda
+                             and key_states.shape[1] * self.num_key_value_groups == query_states.shape[1]
+                             and self.head_dim in (64, 128))
+                if native_ok and past_key_values.device_lengths:
+                    # CUDA-graph friendly step: the row index and the attended length live on the device
+                    kbuf, vbuf, _, ndev = past_key_values.buffers(self.layer_idx)
+                    ops.cache_append(key_states, value_states, kbuf, vbuf, 0, seq_len_dev=ndev, bump=True)
+                    out = ops.decode_attn(query_states[:, :, 0, :], kbuf, vbuf, 0, seq_len_dev=ndev, scale=self.scaling)
+                    attn_output = self.o_proj(out.reshape(input_shape[0], 1, -1))
+                    return attn_output, None
+                key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
+                decode_native = native_ok
         if decode_native:
             # K5: split-K decode attention straight over the pre-allocated compact cache
             kbuf, vbuf, n, _ = past_key_values.buffers(self.layer_idx)
@@ -271,6 +279,49 @@ def replace_mistral(method):
     """baselines/monkeypatch.py:59-102."""
     from transformers.models.mistral import modeling_mistral as mod
     _patch(mod, "Mistral", method, sliding=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA-graphed decode step over the compact cache (SURVEY.md §8f rank 2)
+# ---------------------------------------------------------------------------------------------
+class GraphedDecode:
+    """One decode step (all layers: projections, in-place cache append, K5 attention, MLP, lm_head,
+    greedy argmax) captured once as a CUDA graph and replayed per token.  The cache lengths and the
+    position id live on the device, so replays need no host work at all."""
+
+    def __init__(self, model, cache, first_token, warmup=2):
+        self.model, self.cache = model, cache
+        dev = first_token.device
+        self.tok = first_token.clone()
+        # the reference's benchmark loop passes no position ids: positions continue from the
+        # (compact) layer-0 cache length (benchmark/e2e.py:174)
+        self.pos = torch.full((first_token.shape[0], 1), cache.get_seq_length(), dtype=torch.int64, device=dev)
+        cache.device_lengths = True
+        self.eager_tokens = []
+        for _ in range(warmup):                       # real decode steps, run eagerly (allocations, attributes)
+            self._step()
+            self.eager_tokens.append(self.tok.clone())
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step()
+        # the capture itself did not execute: nothing to undo
+
+    @torch.no_grad()
+    def _step(self):
+        out = self.model(input_ids=self.tok, past_key_values=self.cache, position_ids=self.pos, use_cache=True)
+        self.tok.copy_(out.logits[:, -1, :].argmax(dim=-1, keepdim=True))
+        self.pos.add_(1)
+
+    @torch.no_grad()
+    def generate(self, n):
+        """n more tokens (after the warm-up ones); returns [B, warmup + n] token ids."""
+        toks = list(self.eager_tokens)
+        for _ in range(n):
+            self.graph.replay()
+            toks.append(self.tok.clone())
+        self.cache.sync_lengths()
+        return torch.cat(toks, dim=1)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -100,3 +100,22 @@ def test_snapkv_method_through_the_same_kernels(patched):
     cache = out.past_key_values
     assert cache.get_seq_length(0) == 96 and cache.k[0].shape[1] == 8      # one cache head per query head
     assert torch.isfinite(out.logits).all()
+
+
+def test_graphed_decode_matches_eager_decode(patched):
+    """CUDA-graph replay of the decode step (device-side lengths / positions) == eager loop."""
+    model = _model(torch.bfloat16).to(DEV)
+    patched.set_model(model, _args())
+    ids = torch.randint(0, 211, (2, 700), generator=torch.Generator().manual_seed(6)).to(DEV)
+    eager, cache_e = patched.greedy_generate(model, ids, 9)
+    model.config.fastkv_max_new_tokens = 16
+    model.model.config.fastkv_max_new_tokens = 16
+    with torch.no_grad():
+        out = model(ids, use_cache=True)
+    first = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
+    gd = patched.GraphedDecode(model, out.past_key_values, first, warmup=2)
+    rest = gd.generate(6)
+    got = torch.cat([first, rest], dim=1)
+    assert got.shape == (2, 9)
+    assert torch.equal(got, eager)
+    assert out.past_key_values.get_seq_length(0) == cache_e.get_seq_length(0) == 128 + 8
