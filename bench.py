@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-model", action="store_true")
     ap.add_argument("--score-impl", default="auto", choices=["auto", "simple", "tensor"])
     return ap.parse_args()
 
@@ -388,18 +389,20 @@ def run_ours(args):
         h2d = d2h = 0
         es = 2
         for (l, is_tsp) in plan:
-            h2d += n_prompts * (2 * hkv_local * l * D + hq_local * W * D) * es
+            # K in full, the Q window, and only the C gathered rows of V (read in place from pinned memory)
+            h2d += n_prompts * (hkv_local * l * D + hq_local * W * D + hkv_local * min(cap, l) * D) * es
             d2h += 2 * n_prompts * hkv_local * min(cap, l) * D * es
             if is_tsp and l > tsp_len:
-                h2d += n_prompts * ctx * HIDDEN * es
-                d2h += n_prompts * tsp_len * (8 + HIDDEN * es)
+                h2d += n_prompts * tsp_len * (8 + HIDDEN * es)       # index set + the T gathered hidden rows
+                d2h += n_prompts * tsp_len * (8 + 8 + HIDDEN * es)
 
         def host_step():
             res = None
             for (cl, q, k, v) in host_layers:
                 ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
                 if tsp is not None:
-                    nh, npos = ops.gather_rows(hidden_host.to(dev, non_blocking=True), tsp.to(dev), pos)
+                    # hidden states stay in pinned host memory: only the T selected rows cross the bus
+                    nh, npos = ops.gather_rows(hidden_host, tsp.to(dev, non_blocking=True), pos)
                     res = (nh.cpu(), npos.cpu())
             return res
 
@@ -426,6 +429,27 @@ def run_ours(args):
         cpu = {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                "seconds_per_sample": round(sec, 4)}
 
+    # ---- model-level extras (N == 1): prefill TTFT and decode tok/s of a random-init Llama-3.1-8B-shaped
+    # model through the monkeypatch (the other half of BASELINE.json's metric), reference protocol
+    model_extras = None
+    if rank == 0 and world == 1 and not args.no_model and os.environ.get("FKV_BENCH_MODEL", "1") != "0":
+        try:
+            del layers, hidden
+            if not args.no_e2e:
+                del host_layers, hidden_host, q_host
+            graph = sgraph = None
+            torch.cuda.empty_cache()
+            import types as _types
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import model_bench
+            margs = _types.SimpleNamespace(model="llama", method="fastkv", ctx=ctx, batch=1, genlen=64, capacity=cap,
+                                           tsp_len=tsp_len, tsp_idx=TSP_IDX, layers=0, runs=1, graph=True)
+            import io, contextlib
+            with contextlib.redirect_stdout(io.StringIO()):
+                model_extras = model_bench.run(margs)
+        except Exception as e:  # noqa: BLE001
+            model_extras = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -436,7 +460,7 @@ def run_ours(args):
             "timed_with": "cuda-graph replay of the C-ABI launches" if graph is not None else "eager C-ABI launches",
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "model": model_extras,
         }
         print(json.dumps(line))
     if world > 1:

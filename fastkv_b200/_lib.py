@@ -203,6 +203,14 @@ def require_cuda(*tensors):
             raise RuntimeError("fastkv_b200 has no CPU path: tensors must live on a CUDA device")
 
 
+def require_cuda_or_pinned(*tensors):
+    """Gather SOURCES may also be page-locked host memory: the kernels then read only the selected
+    rows over PCIe/NVLink-C2C (zero-copy) instead of the caller staging the whole tensor."""
+    for t in tensors:
+        if t is not None and not t.is_cuda and not (hasattr(t, "is_pinned") and t.is_pinned()):
+            raise RuntimeError("fastkv_b200 has no CPU path: tensors must live on a CUDA device (or pinned host memory for gather sources)")
+
+
 _workspaces = {}
 
 

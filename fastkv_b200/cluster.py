@@ -16,6 +16,13 @@ from . import _lib as L
 from . import ops
 
 
+def _to_pinned_host(t: torch.Tensor) -> torch.Tensor:
+    """Device result -> page-locked host tensor (asynchronous; the caller synchronises once)."""
+    out = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+    out.copy_(t, non_blocking=True)
+    return out
+
+
 def _stage_to_device(t: torch.Tensor, device: torch.device) -> torch.Tensor:
     """Host buffer -> device (the e2e path of bench.py): pinned memory copies asynchronously."""
     return t.to(device, non_blocking=True)
@@ -79,7 +86,10 @@ class FastKVCluster:
             q_win = _stage_to_device(query_states[:, :, q_len - w:, :], dev)
             query_states = _RowOffsetView(q_win.contiguous(), q_len)
             key_states = _stage_to_device(key_states, dev)
-            value_states = _stage_to_device(value_states, dev)
+            # V is only ever gathered (C rows per head): page-locked V stays on the host and the
+            # compaction kernel reads just those rows; pageable V has to be staged
+            if not value_states.is_pinned():
+                value_states = _stage_to_device(value_states, dev)
         else:
             L.require_cuda(key_states, query_states, value_states)
 
@@ -97,8 +107,9 @@ class FastKVCluster:
             if self.keep_aux:
                 self.last_aux = res[3]
         if host_io:
-            k, v = k.cpu(), v.cpu()
-            tsp = tsp.cpu() if tsp is not None else None
+            k, v = _to_pinned_host(k), _to_pinned_host(v)
+            tsp = _to_pinned_host(tsp) if tsp is not None else None
+            torch.cuda.current_stream().synchronize()      # results are on the host when we return
         return k, v, tsp
 
     def _update_kv_sharded(self, key_states, query_states, value_states):

@@ -35,12 +35,29 @@ gather_kv_kernel(GatherKvArgs a) {
   char* vob = a.vo + b * a.vo_sb + hs * a.vo_sh;
   const int r0 = blockIdx.x * a.rows_per_cta;
   const int r1 = min(r0 + a.rows_per_cta, C);
-  for (int r = r0 + row_in_cta; r < r1; r += rows_par) {
-    const int64_t src_row = (r < a.n_sel) ? idx[r] : (int64_t)(a.L - a.W + (r - a.n_sel));
-    const uint4 kv = ld_stream16(kb + src_row * a.k_sl + lane_chunk * 16);
-    const uint4 vv = ld_stream16(vb + src_row * a.v_sl + lane_chunk * 16);
-    st_stream16(kob + (int64_t)r * a.ko_sl + lane_chunk * 16, kv);
-    st_stream16(vob + (int64_t)r * a.vo_sl + lane_chunk * 16, vv);
+  // 4 rows per thread per round: all index loads, then all 8 payload loads, then the 8 stores, so
+  // every thread keeps 128 bytes in flight (the copy is pure latency otherwise)
+  for (int rb = r0 + row_in_cta; rb < r1; rb += rows_par * 4) {
+    int64_t src_row[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = rb + u * rows_par;
+      src_row[u] = (r < r1) ? ((r < a.n_sel) ? idx[r] : (int64_t)(a.L - a.W + (r - a.n_sel))) : -1;
+    }
+    uint4 kv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (src_row[u] >= 0) {
+        kv[u] = ld_stream16(kb + src_row[u] * a.k_sl + lane_chunk * 16);
+        vv[u] = ld_stream16(vb + src_row[u] * a.v_sl + lane_chunk * 16);
+      }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (src_row[u] >= 0) {
+        const int r = rb + u * rows_par;
+        st_stream16(kob + (int64_t)r * a.ko_sl + lane_chunk * 16, kv[u]);
+        st_stream16(vob + (int64_t)r * a.vo_sl + lane_chunk * 16, vv[u]);
+      }
   }
 }
 

@@ -97,7 +97,8 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, *, window_siz
               head_range: Optional[Tuple[int, int]] = None, head_div: int = 1,
               k_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None):
     """Compact K/V rows selected by ``idx`` [B,Hsel,n_sel] and append the last W rows."""
-    L.require_cuda(k, v, idx)
+    L.require_cuda(idx)
+    L.require_cuda_or_pinned(k, v)
     lib = L.load()
     B, _, Lk, D = k.shape
     Hsel, n_sel = idx.shape[1], idx.shape[2]
@@ -122,14 +123,15 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, *, window_siz
 
 def gather_rows(hidden: torch.Tensor, idx: torch.Tensor, position_ids: Optional[torch.Tensor] = None):
     """hidden [B,L,H] -> [B,T,H] rows picked by idx [B,T]; optionally position_ids [B|1, L] -> [B,T]."""
-    L.require_cuda(hidden, idx, position_ids)
+    L.require_cuda(idx, position_ids)
+    L.require_cuda_or_pinned(hidden)
     lib = L.load()
     B, Ln, H = hidden.shape
     T = idx.shape[1]
     if hidden.stride(2) != 1 or idx.dtype != torch.int64 or idx.stride(1) != 1:
         raise ValueError("fastkv_b200: hidden needs a contiguous last dim and idx must be int64")
     es = hidden.element_size()
-    out = torch.empty((B, T, H), dtype=hidden.dtype, device=hidden.device)
+    out = torch.empty((B, T, H), dtype=hidden.dtype, device=idx.device)
     p = L.GatherRowsParams()
     p.struct_size = C.sizeof(L.GatherRowsParams)
     p.B, p.L, p.T, p.row_bytes = B, Ln, T, H * es
@@ -140,11 +142,11 @@ def gather_rows(hidden: torch.Tensor, idx: torch.Tensor, position_ids: Optional[
     if position_ids is not None:
         if position_ids.dtype != torch.int64 or position_ids.dim() != 2 or position_ids.stride(1) != 1:
             raise ValueError("fastkv_b200: position_ids must be int64 [B or 1, L]")
-        pos_out = torch.empty((B, T), dtype=torch.int64, device=hidden.device)
+        pos_out = torch.empty((B, T), dtype=torch.int64, device=idx.device)
         p.pos_in = position_ids.data_ptr()
         p.pos_stride_b = position_ids.stride(0) if position_ids.shape[0] == B and B > 1 else 0
         p.pos_out, p.pos_out_stride_b = pos_out.data_ptr(), pos_out.stride(0)
-    L.check(lib.fkv_gather_rows(C.byref(p), L.stream_ptr(hidden.device)))
+    L.check(lib.fkv_gather_rows(C.byref(p), L.stream_ptr(idx.device)))
     return (out, pos_out) if position_ids is not None else out
 
 
@@ -198,7 +200,8 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
 
     Returns (k_out [B,Hsel,C,D], v_out, tsp_idx [B,T] | None) and, with ``return_aux``, a dict with
     the scores [B,Hsel,P], per-head indices [B,Hsel,C-W] and (TSP) importance [B,P]."""
-    L.require_cuda(q, k, v)
+    L.require_cuda(q, k)
+    L.require_cuda_or_pinned(v)
     lib = L.load()
     B, Hq, Lq, D = q.shape
     Hkv = k.shape[1]
