@@ -246,21 +246,22 @@ topk_row_kernel(TopkArgs a) {
 }
 
 // ---- cluster fast path -------------------------------------------------------------------------------
-constexpr int kSliceKeys = 32768;                 // keys per CTA, held in shared memory
+constexpr int kSliceKeys = 16384;                 // keys per CTA, held in shared memory
 constexpr int kKeysPadded = kSliceKeys + kSliceKeys / 32;   // one pad word per 32 keys: conflict-free blocked reads
-constexpr int kSortHalf = 2048;                   // capacity of each of the two sort regions
+constexpr int kTargetKeys = 4096;                 // preferred keys per CTA (more CTAs per row = shorter phases)
+constexpr int kKmax = 2048;                       // largest k served by the cluster path
 
 struct ClusterSmem {
   uint32_t keys[kKeysPadded];       // order-preserving keys of this CTA's slice
-  uint32_t hist[kMaxBins];          // local 12-bit histogram; leader: second-level histogram
+  uint32_t hist[kMaxBins];          // local 12-bit histogram; leader: adaptive-bin counts / cursors
+  uint32_t ghist[kMaxBins];         // leader: cluster-wide 12-bit histogram (remote atomics from every CTA)
   unsigned long long cand[kCandMax];     // leader: gathered candidates (unordered)
   unsigned long long sortbuf[kCandMax];  // leader: candidates grouped by adaptive bin (also the generic path's sort buffer)
   uint16_t bbase[kMaxBins];         // leader: candidates in higher adaptive bins (<= 4096)
-  uint32_t sub[kMaxCluster];        // per-owner subtotals
   uint32_t cnt_cta[kMaxCluster];    // INDEX_ASC: selected count per CTA
   uint32_t wsum[kWarps];
-  uint32_t bc[12];                  // [0] bin*, [1] count above bin*, [2] count in bin*, [3] gather cursor,
-                                    // [4..5] k-th composite (lo, hi), [6] sub-bin*, [7] nA cursor, [8] nB cursor, [9] need in sub-bin
+  uint32_t bc[16];                  // [0] bin*, [1] count above bin*, [2] count in bin*, [3] gather cursor,
+                                    // [4..5] k-th composite (lo, hi), [6] top non-empty bin, [11] fallback flag
 };
 
 __device__ inline int key_slot(int i) { return i + (i >> 5); }
@@ -298,12 +299,13 @@ topk_cluster_kernel(TopkArgs a) {
   const int n = a.n, k = a.k;
   int64_t* out = a.out + (int64_t)row * a.out_stride_row;
   auto csync = [&]() { if (multi) cluster.sync(); else __syncthreads(); };
+  ClusterSmem& lead = multi ? *cluster.map_shared_rank(&sm, 0) : sm;   // the leader CTA's shared memory
 
-  for (int i = tid; i < kMaxBins; i += kThreads) sm.hist[i] = 0;
-  if (tid < 12) sm.bc[tid] = 0;
-  __syncthreads();
+  for (int i = tid; i < kMaxBins; i += kThreads) { sm.hist[i] = 0; sm.ghist[i] = 0; }
+  if (tid < 16) sm.bc[tid] = 0;
+  csync();                                          // the leader's ghist is zero before anybody adds to it
 
-  // ---- 1. load the slice (fixed-order head sum for TSP), keys -> smem, 12-bit histogram ---------------
+  // ---- 1. load the slice (fixed-order head sum for TSP), keys -> smem ---------------------------------
   const int per_cta = ((n + C - 1) / C + 3) & ~3;
   const int base = crank * per_cta;
   const int cnt = max(0, min(n, base + per_cta) - base);       // keys of this CTA
@@ -357,7 +359,7 @@ topk_cluster_kernel(TopkArgs a) {
     }
   }
   __syncthreads();
-  // 12-bit histogram with run-length aggregation: neighbouring keys usually share a bin, so a warp
+  // 12-bit histogram with run-length aggregation: neighbouring keys often share a bin, so a warp
   // issues one shared-memory atomic per run instead of one per key
   for (int i0 = 0; i0 < cnt; i0 += kThreads) {
     const int i = i0 + tid;
@@ -371,55 +373,42 @@ topk_cluster_kernel(TopkArgs a) {
       atomicAdd(&sm.hist[bin], (uint32_t)len);
     }
   }
+  __syncthreads();
   TK_TRACE(1);
-  csync();
-  TK_TRACE(2);
 
-  // ---- 2. reduce histograms (owner = CTA crank for bins [crank*nbo, (crank+1)*nbo)), find bin* --------
-  const int nbo = kMaxBins / C;
-  uint32_t my_tot[4] = {0, 0, 0, 0};                // owned bins, top-down: b = hi - (4 tid + i)
-  uint32_t lsum = 0;
-  const int hi = (crank + 1) * nbo - 1;
+  // ---- 2. cluster histogram in the leader (only the few non-empty bins travel), leader finds bin* ------
   if (multi) {
-    uint32_t part[4][kMaxCluster];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int c = 0; c < kMaxCluster; ++c)
-        part[i][c] = (tid * 4 + i < nbo && c < C) ? cluster.map_shared_rank(sm.hist, c)[hi - (tid * 4 + i)] : 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int c = 0; c < kMaxCluster; ++c) my_tot[i] += part[i][c];
-      lsum += my_tot[i];
+      const uint32_t c = sm.hist[tid * 4 + i];
+      if (c) atomicAdd(&lead.ghist[tid * 4 + i], c);
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { my_tot[i] = sm.hist[hi - (tid * 4 + i)]; lsum += my_tot[i]; }
-  }
-  uint32_t own_total;
-  const uint32_t incl = block_scan_incl(lsum, sm.wsum, own_total);
-  if (multi) {
-    if (tid < C) cluster.map_shared_rank(sm.sub, tid)[crank] = own_total;
     cluster.sync();
   }
-  {
-    uint32_t above_owner = 0;
-    for (int c = C - 1; c > crank; --c) above_owner += sm.sub[c];
-    const uint32_t excl = above_owner + incl - lsum;
-    if (excl < (uint32_t)k && (uint32_t)k <= excl + lsum) {    // the k-th key is in one of my 4 bins
-      uint32_t above = excl;
+  TK_TRACE(2);
+  if (crank == 0) {
+    const uint32_t* gh = multi ? sm.ghist : sm.hist;
+    uint32_t local[4], ls = 0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (above < (uint32_t)k && (uint32_t)k <= above + my_tot[i]) {
-          for (int c = 0; c < C; ++c) {
-            uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, c) : sm.bc;
-            rbc[0] = (uint32_t)(hi - (tid * 4 + i));
-            rbc[1] = above;
-            rbc[2] = my_tot[i];
-          }
-        }
-        above += my_tot[i];
+    for (int i = 0; i < 4; ++i) { local[i] = gh[kMaxBins - 1 - (tid * 4 + i)]; ls += local[i]; }
+    uint32_t total;
+    const uint32_t incl = block_scan_incl(ls, sm.wsum, total);
+    uint32_t above = incl - ls;
+    uint32_t b_star = 0, n_ab = 0, n_in = 0;
+    bool found = false;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (above < (uint32_t)k && (uint32_t)k <= above + local[i]) {
+        found = true; b_star = (uint32_t)(kMaxBins - 1 - (tid * 4 + i)); n_ab = above; n_in = local[i];
+      }
+      if (above == 0 && local[i] != 0)                                // first non-empty bin from the top
+        sm.bc[6] = (uint32_t)(kMaxBins - 1 - (tid * 4 + i));
+      above += local[i];
+    }
+    if (found) {
+      for (int c = 0; c < C; ++c) {
+        uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, c) : sm.bc;
+        rbc[0] = b_star; rbc[1] = n_ab; rbc[2] = n_in;
       }
     }
   }
@@ -442,58 +431,45 @@ topk_cluster_kernel(TopkArgs a) {
     return;
   }
 
-  // ---- 3. send candidates (bin >= bin*) to the leader -------------------------------------------------
+  // ---- 3. send candidates (bin >= bin*) to the leader: count, one cursor atomic per warp, write ------
   {
-    uint32_t* cursor = multi ? &cluster.map_shared_rank(sm.bc, 0)[3] : &sm.bc[3];
-    unsigned long long* lcand = multi ? cluster.map_shared_rank(sm.cand, 0) : sm.cand;
-    // pass 1: how many candidates does this warp hold?  pass 2: one cursor atomic per warp, then write
-    uint32_t wcount = 0;
-    for (int i0 = 0; i0 < cnt; i0 += kThreads) {
-      const int i = i0 + tid;
-      const bool take = (i < cnt) && ((sm.keys[key_slot(i)] >> 20) >= bin_star);
-      wcount += __popc(__ballot_sync(0xffffffffu, take));
+    uint32_t mine = 0;
+    for (int i = tid; i < cnt; i += kThreads) mine += ((sm.keys[key_slot(i)] >> 20) >= bin_star);
+    uint32_t pre = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
     }
+    const uint32_t warp_total = __shfl_sync(0xffffffffu, pre, 31);
     uint32_t wbase = 0;
-    if (lane == 0 && wcount) wbase = atomicAdd(cursor, wcount);
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    for (int i0 = 0; i0 < cnt; i0 += kThreads) {
-      const int i = i0 + tid;
-      const uint32_t key = (i < cnt) ? sm.keys[key_slot(i)] : 0u;
-      const bool take = (i < cnt) && ((key >> 20) >= bin_star);
-      const uint32_t m = __ballot_sync(0xffffffffu, take);
-      if (take)
-        lcand[wbase + __popc(m & ((1u << lane) - 1))] =
-            ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
-      wbase += __popc(m);
+    if (lane == 31 && warp_total) wbase = atomicAdd(&lead.bc[3], warp_total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    uint32_t pos = wbase + pre - mine;
+    for (int i = tid; i < cnt; i += kThreads) {
+      const uint32_t key = sm.keys[key_slot(i)];
+      if ((key >> 20) >= bin_star)
+        lead.cand[pos++] = ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
     }
   }
   csync();
   TK_TRACE(4);
 
   // ---- 4. leader: rank the candidates without a general sort ------------------------------------------
-  // Counting scatter on 4096 ADAPTIVE bins (the candidates' key range [bin* << 20, max key] mapped
-  // linearly onto the bins, so a bin holds ~1 key), then every candidate counts the larger keys in
-  // its own bin: rank = keys in higher bins + larger keys in the bin.  A skewed row (a bin with
-  // more than 64 keys, e.g. exact ties) takes the bitonic sort instead.
+  // Counting scatter on 4096 ADAPTIVE bins (the candidates' key range mapped linearly onto the bins,
+  // so a bin holds ~1 key), then every candidate counts the larger keys in its own bin:
+  // rank = keys in higher bins + larger keys in the bin.  A skewed row (a bin with more than 64
+  // keys, e.g. exact ties) takes the bitonic sort instead.
   if (crank == 0) {
     uint32_t* cursor = sm.hist;
-    uint16_t* bbase = sm.bbase;                                         // keys in higher bins
+    uint16_t* bbase = sm.bbase;
     unsigned long long* grouped = sm.sortbuf;
-    // block max of the candidate keys
-    uint32_t kmax = 0;
-    for (int i = tid; i < (int)n_cand; i += kThreads) kmax = max(kmax, (uint32_t)(sm.cand[i] >> 32));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
-    if (lane == 0) sm.wsum[tid >> 5] = kmax;
-    __syncthreads();
-    kmax = sm.wsum[lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     const uint32_t klo = bin_star << 20;
-    const unsigned long long range = (unsigned long long)(kmax - klo) + 1ull;
+    const uint32_t khi = (sm.bc[6] << 20) | 0xfffffu;                   // upper bound of the top non-empty 12-bit bin
+    const unsigned long long range = (unsigned long long)(khi - klo) + 1ull;
     const unsigned long long mult = (((unsigned long long)kMaxBins << 32) - 1ull) / range;   // bin = ((key-klo)*mult) >> 32 < 4096
     auto fine_bin = [&](uint32_t key) { return (uint32_t)(((unsigned long long)(key - klo) * mult) >> 32); };
+    for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
     __syncthreads();
     for (int i = tid; i < (int)n_cand; i += kThreads) atomicAdd(&cursor[fine_bin((uint32_t)(sm.cand[i] >> 32))], 1u);
     __syncthreads();
@@ -511,36 +487,32 @@ topk_cluster_kernel(TopkArgs a) {
         const int b = kMaxBins - 1 - (tid * 4 + i);
         bbase[b] = (uint16_t)above;
         above += local[i];
+        cursor[b] = 0;                              // becomes the scatter cursor (each thread owns its 4 bins here)
       }
     }
     __syncthreads();
     unsigned long long kth = 0ull;
     if (!skew) {
-      {
-        for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
-        __syncthreads();
-        for (int i = tid; i < (int)n_cand; i += kThreads) {
-          const unsigned long long c = sm.cand[i];
-          const uint32_t b = fine_bin((uint32_t)(c >> 32));
-          grouped[bbase[b] + atomicAdd(&cursor[b], 1u)] = c;
-        }
-        __syncthreads();
-        for (int i = tid; i < (int)n_cand; i += kThreads) {
-          const unsigned long long c = grouped[i];
-          const uint32_t b = fine_bin((uint32_t)(c >> 32));
-          const uint32_t s0 = bbase[b], s1 = s0 + cursor[b];
-          uint32_t rank = s0;
-          for (uint32_t q = s0; q < s1; ++q) rank += (grouped[q] > c);
-          if (rank < (uint32_t)k) {
-            if (by_value) out[rank] = (int64_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
-            if (rank == (uint32_t)k - 1) { sm.bc[4] = (uint32_t)(c & 0xffffffffull); sm.bc[5] = (uint32_t)(c >> 32); }
-          }
-        }
-        __syncthreads();
-        kth = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
+      for (int i = tid; i < (int)n_cand; i += kThreads) {
+        const unsigned long long c = sm.cand[i];
+        const uint32_t b = fine_bin((uint32_t)(c >> 32));
+        grouped[bbase[b] + atomicAdd(&cursor[b], 1u)] = c;
       }
-    }
-    if (skew) {
+      __syncthreads();
+      for (int i = tid; i < (int)n_cand; i += kThreads) {
+        const unsigned long long c = grouped[i];
+        const uint32_t b = fine_bin((uint32_t)(c >> 32));
+        const uint32_t s0 = bbase[b], s1 = s0 + cursor[b];
+        uint32_t rank = s0;
+        for (uint32_t q = s0; q < s1; ++q) rank += (grouped[q] > c);
+        if (rank < (uint32_t)k) {
+          if (by_value) out[rank] = (int64_t)(0xffffffffu - (uint32_t)(c & 0xffffffffull));
+          if (rank == (uint32_t)k - 1) { sm.bc[4] = (uint32_t)(c & 0xffffffffull); sm.bc[5] = (uint32_t)(c >> 32); }
+        }
+      }
+      __syncthreads();
+      kth = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
+    } else {
       int cap = 1;
       while (cap < (int)n_cand) cap <<= 1;
       for (int i = (int)n_cand + tid; i < cap; i += kThreads) sm.cand[i] = 0ull;
@@ -562,12 +534,11 @@ topk_cluster_kernel(TopkArgs a) {
   }
   TK_TRACE(5);
   csync();
-  if (sm.bc[11]) goto fallback;                     // uniform across the cluster
   if (by_value) return;
 
   // ---- 5. INDEX_ASC: every CTA compacts its own selected keys in index order ---------------------------
   const unsigned long long thr = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
-  constexpr int kPerThread = kSliceKeys / kThreads;               // 32 consecutive keys per thread
+  constexpr int kPerThread = kSliceKeys / kThreads;               // 16 consecutive keys per thread
   uint32_t mine = 0;
   uint32_t selmask = 0;
 #pragma unroll
@@ -625,14 +596,11 @@ int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
   const bool by_value = p.order == FKV_ORDER_VALUE_DESC;
 
   static const bool no_cluster = getenv("FKV_TOPK_NO_CLUSTER") != nullptr;
-  // CTAs per row: enough for the slice to fit (32768 keys per CTA) and, for summed rows (TSP), enough
-  // to spread the nsum-fold read over several SMs
-  int C = ceil_div(p.n, kSliceKeys);
-  if (a.nsum > 1 && C <= kMaxCluster) {
-    const long long want = ((long long)p.n * a.nsum + kSliceKeys - 1) / kSliceKeys;
-    C = (int)(want > kMaxCluster ? kMaxCluster : (want > C ? want : C));
-  }
-  if (!no_cluster && C <= kMaxCluster && p.k <= kSortHalf && (p.src_stride_row % 4) == 0) {
+  // CTAs per row: ~4096 keys per CTA (short phases), at least enough for the slice to fit in smem
+  long long want = ((long long)p.n * a.nsum + kTargetKeys - 1) / kTargetKeys;   // summed rows read nsum x the bytes
+  int C = (int)(want > kMaxCluster ? kMaxCluster : (want < 1 ? 1 : want));
+  const bool fits = ceil_div(p.n, kMaxCluster) <= kSliceKeys;
+  if (!no_cluster && fits && p.k <= kKmax && (p.src_stride_row % 4) == 0) {
     int Cp = 1;
     while (Cp < C) Cp <<= 1;                        // cluster sizes 1, 2, 4, 8 (divides the 4096 bins)
     a.cluster = Cp;
