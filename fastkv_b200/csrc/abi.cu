@@ -234,7 +234,14 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   tk.src = sp.score; tk.src_stride_row = P; tk.src_stride_sum = 0;
   tk.out = p->idx_out; tk.out_stride_row = n_sel;
   tk.workspace = ws + score_ws; tk.workspace_bytes = head_ws;
-  if ((rc = launch_topk(tk, s)) != FKV_OK) return rc;
+  fkv_gather_kv_params g{};
+  g.struct_size = sizeof(g);
+  g.dtype = sp.dtype; g.B = sp.B; g.L = sp.L; g.D = sp.D; g.window_size = W; g.n_sel = n_sel;
+  g.h0 = sp.h0; g.h1 = sp.h1; g.head_div = sp.mode == FKV_MODE_SNAPKV ? sp.Hq / sp.Hkv : 1;
+  g.k = sp.k; g.v = p->v; g.idx = p->idx_out; g.idx_stride_b = (int64_t)Hsel * n_sel; g.idx_stride_h = n_sel;
+  g.k_out = p->k_out; g.v_out = p->v_out;
+  bool fused = false;
+  if ((rc = launch_topk_fused(tk, g, &fused, s)) != FKV_OK) return rc;     // K3 (+ K4 when the cluster kernel runs)
 
   if (p->tsp_k > 0) {
     fkv_topk_params tt{};
@@ -246,14 +253,7 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
     tt.workspace = ws + score_ws + head_ws; tt.workspace_bytes = tsp_ws;
     if ((rc = launch_topk(tt, s)) != FKV_OK) return rc;
   }
-
-  fkv_gather_kv_params g{};
-  g.struct_size = sizeof(g);
-  g.dtype = sp.dtype; g.B = sp.B; g.L = sp.L; g.D = sp.D; g.window_size = W; g.n_sel = n_sel;
-  g.h0 = sp.h0; g.h1 = sp.h1; g.head_div = sp.mode == FKV_MODE_SNAPKV ? sp.Hq / sp.Hkv : 1;
-  g.k = sp.k; g.v = p->v; g.idx = p->idx_out; g.idx_stride_b = (int64_t)Hsel * n_sel; g.idx_stride_h = n_sel;
-  g.k_out = p->k_out; g.v_out = p->v_out;
-  return launch_gather_kv(g, s);
+  return fused ? FKV_OK : launch_gather_kv(g, s);
 }
 
 }  // extern "C"

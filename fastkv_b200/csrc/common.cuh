@@ -106,6 +106,8 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s);
 bool score_tensor_supported(const fkv_score_params& p);
 size_t score_workspace_bytes(int mode, int B, int Hq, int Hkv, int L, int W);
 int launch_topk(const fkv_topk_params& p, cudaStream_t s);
+// per-head selection with the KV compaction fused behind it when the cluster kernel is used (*fused)
+int launch_topk_fused(const fkv_topk_params& p, const fkv_gather_kv_params& g, bool* fused, cudaStream_t s);
 size_t topk_workspace_bytes(int rows, int n, int k);
 int launch_gather_kv(const fkv_gather_kv_params& p, cudaStream_t s);
 int launch_gather_rows(const fkv_gather_rows_params& p, cudaStream_t s);

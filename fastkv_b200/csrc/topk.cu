@@ -42,6 +42,13 @@ __device__ inline uint32_t ordered_key(float x) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// optional KV compaction fused behind the per-head selection (K3 + K4 in one launch)
+struct FusedGather {
+  const char* k; const char* v; char* ko; char* vo;
+  int64_t k_sb, k_sh, k_sl, v_sb, v_sh, v_sl, ko_sb, ko_sh, ko_sl, vo_sb, vo_sh, vo_sl;   // bytes
+  int L, W, h0, head_div, Hsel, row_chunks, enabled;
+};
+
 struct TopkArgs {
   const float* src; int64_t src_stride_row, src_stride_sum;
   int n, k, order, tail, nsum;
@@ -52,6 +59,7 @@ struct TopkArgs {
   int cluster;             // CTAs per row (cluster path)
   int write_dense;         // cluster path: also store the summed row (importance output)
   unsigned long long* trace;   // FKV_TOPK_TRACE debugging aid
+  FusedGather g;
 };
 
 // Inclusive block scan of one uint32 per thread (kThreads threads); returns inclusive value and
@@ -427,6 +435,20 @@ topk_cluster_kernel(TopkArgs a) {
     if (crank == 0) {
       const float* x = (a.nsum > 1) ? a.dense + (int64_t)row * n : src;
       select_row_generic(x, n, k, a.order, a.tail, out, sm.hist, sm.wsum, sm.bc, sm.sortbuf, a.sort_cap);
+      if (a.g.enabled && by_value) {                // fused compaction on the fallback path: leader only
+        __syncthreads();
+        const FusedGather& g = a.g;
+        const int b = row / g.Hsel, hs = row - b * g.Hsel;
+        const int src_head = (g.h0 + hs) / g.head_div;
+        const int lane_chunk = tid % g.row_chunks, rows_par = kThreads / g.row_chunks;
+        for (int r = tid / g.row_chunks; r < k + g.W; r += rows_par) {
+          const int64_t sr = (r < k) ? out[r] : (int64_t)(g.L - g.W + (r - k));
+          st_stream16(g.ko + b * g.ko_sb + hs * g.ko_sh + (int64_t)r * g.ko_sl + lane_chunk * 16,
+                      ld_stream16(g.k + b * g.k_sb + src_head * g.k_sh + sr * g.k_sl + lane_chunk * 16));
+          st_stream16(g.vo + b * g.vo_sb + hs * g.vo_sh + (int64_t)r * g.vo_sl + lane_chunk * 16,
+                      ld_stream16(g.v + b * g.v_sb + src_head * g.v_sh + sr * g.v_sl + lane_chunk * 16));
+        }
+      }
     }
     return;
   }
@@ -534,7 +556,46 @@ topk_cluster_kernel(TopkArgs a) {
   }
   TK_TRACE(5);
   csync();
-  if (by_value) return;
+  if (by_value) {
+    if (a.g.enabled) {
+      // ---- 4b. fused KV compaction (baselines/fastkv/utils.py:114-121): the whole cluster copies the
+      // selected rows of this (batch, head) + the W window rows; indices come from `out` (global,
+      // visible cluster-wide after the barrier above)
+      const FusedGather& g = a.g;
+      const int b = row / g.Hsel, hs = row - b * g.Hsel;
+      const int src_head = (g.h0 + hs) / g.head_div;
+      const char* kb = g.k + b * g.k_sb + src_head * g.k_sh;
+      const char* vb = g.v + b * g.v_sb + src_head * g.v_sh;
+      char* kob = g.ko + b * g.ko_sb + hs * g.ko_sh;
+      char* vob = g.vo + b * g.vo_sb + hs * g.vo_sh;
+      const int rows_total = k + g.W;
+      const int lane_chunk = tid % g.row_chunks, row_in_cta = tid / g.row_chunks;
+      const int rows_par = kThreads / g.row_chunks;
+      for (int rb = crank * rows_par + row_in_cta; rb < rows_total; rb += 4 * rows_par * C) {
+        int64_t sr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int r = rb + u * rows_par * C;
+          sr[u] = (r < rows_total) ? ((r < k) ? __ldcg(out + r) : (int64_t)(g.L - g.W + (r - k))) : -1;
+        }
+        uint4 kv[4], vv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (sr[u] >= 0) {
+            kv[u] = ld_stream16(kb + sr[u] * g.k_sl + lane_chunk * 16);
+            vv[u] = ld_stream16(vb + sr[u] * g.v_sl + lane_chunk * 16);
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (sr[u] >= 0) {
+            const int r = rb + u * rows_par * C;
+            st_stream16(kob + (int64_t)r * g.ko_sl + lane_chunk * 16, kv[u]);
+            st_stream16(vob + (int64_t)r * g.vo_sl + lane_chunk * 16, vv[u]);
+          }
+      }
+    }
+    return;
+  }
 
   // ---- 5. INDEX_ASC: every CTA compacts its own selected keys in index order ---------------------------
   const unsigned long long thr = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
@@ -577,7 +638,16 @@ size_t topk_workspace_bytes(int rows, int n, int k) {
   return b + 256;
 }
 
-int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
+static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params* fg, bool* fused, cudaStream_t s);
+
+int launch_topk(const fkv_topk_params& p, cudaStream_t s) { return launch_topk_impl(p, nullptr, nullptr, s); }
+
+int launch_topk_fused(const fkv_topk_params& p, const fkv_gather_kv_params& g, bool* fused, cudaStream_t s) {
+  return launch_topk_impl(p, &g, fused, s);
+}
+
+static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params* fg, bool* fused, cudaStream_t s) {
+  if (fused) *fused = false;
   TopkArgs a{};
   a.src = p.src; a.src_stride_row = p.src_stride_row; a.src_stride_sum = p.src_stride_sum;
   a.n = p.n; a.k = p.k; a.order = p.order; a.tail = p.tail; a.nsum = p.nsum < 1 ? 1 : p.nsum;
@@ -604,6 +674,20 @@ int launch_topk(const fkv_topk_params& p, cudaStream_t s) {
     int Cp = 1;
     while (Cp < C) Cp <<= 1;                        // cluster sizes 1, 2, 4, 8 (divides the 4096 bins)
     a.cluster = Cp;
+    if (fg && by_value && Cp >= 4) {                  // enough CTAs per row for the copy to be worth fusing
+      const int es = dtype_size(fg->dtype);
+      FusedGather& g = a.g;
+      g.k = (const char*)fg->k.ptr; g.v = (const char*)fg->v.ptr;
+      g.ko = (char*)const_cast<void*>(fg->k_out.ptr); g.vo = (char*)const_cast<void*>(fg->v_out.ptr);
+      g.k_sb = fg->k.stride_b * es; g.k_sh = fg->k.stride_h * es; g.k_sl = fg->k.stride_l * es;
+      g.v_sb = fg->v.stride_b * es; g.v_sh = fg->v.stride_h * es; g.v_sl = fg->v.stride_l * es;
+      g.ko_sb = fg->k_out.stride_b * es; g.ko_sh = fg->k_out.stride_h * es; g.ko_sl = fg->k_out.stride_l * es;
+      g.vo_sb = fg->v_out.stride_b * es; g.vo_sh = fg->v_out.stride_h * es; g.vo_sl = fg->v_out.stride_l * es;
+      g.L = fg->L; g.W = fg->window_size; g.h0 = fg->h0; g.head_div = fg->head_div; g.Hsel = fg->h1 - fg->h0;
+      g.row_chunks = fg->D * es / 16;
+      g.enabled = 1;
+      if (fused) *fused = true;
+    }
     a.write_dense = (a.nsum > 1);                   // the fallback inside the kernel needs the dense row
     static bool attr_set = false;
     if (!attr_set) {
