@@ -286,7 +286,7 @@ def run_ours(args):
     c0 = lib.fkv_launch_count()
     one_step()
     launches_per_step = lib.fkv_launch_count() - c0
-    use_graph = (not args.no_graph) and world == 1
+    use_graph = (not args.no_graph) and world == 1   # graph capture around NCCL hung at teardown in testing: eager launches for N > 1
     graph = None
     if use_graph:
         try:
