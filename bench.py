@@ -260,13 +260,16 @@ def run_ours(args):
     hidden = torch.randn(n_prompts, ctx, HIDDEN, generator=gen, device=dev, dtype=torch.bfloat16)
     pos = torch.arange(ctx, device=dev).unsqueeze(0)
 
-    def one_step():
+    def run_layers(sel):
         out = None
-        for (cl, q, k, v) in layers:
+        for (cl, q, k, v) in sel:
             ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
             if tsp is not None:
                 out = ops.gather_rows(hidden, tsp, pos)
         return out
+
+    def one_step():
+        return run_layers(layers)
 
     bytes_step = 0
     for (l, is_tsp) in plan:
@@ -286,20 +289,45 @@ def run_ours(args):
     c0 = lib.fkv_launch_count()
     one_step()
     launches_per_step = lib.fkv_launch_count() - c0
-    use_graph = (not args.no_graph) and world == 1   # graph capture around NCCL hung at teardown in testing: eager launches for N > 1
+    # CUDA-graph replay so that host launch latency is not what gets timed.  N == 1: the whole step is
+    # one graph.  N > 1: the layers without a collective are captured as two graphs around the TSP
+    # layer, whose NCCL exchange runs eagerly (capturing NCCL hung at teardown in testing).
     graph = None
-    if use_graph:
+    timed_with = "eager C-ABI launches"
+    run = one_step
+    if not args.no_graph:
         try:
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                one_step()
-            graph.replay()
-            torch.cuda.synchronize()
+            if world == 1:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    one_step()
+                graph.replay()
+                torch.cuda.synchronize()
+                run = graph.replay
+                timed_with = "cuda-graph replay of the C-ABI launches"
+            else:
+                tsp_pos = [i for i, (l, t) in enumerate(plan) if t][0]
+                pre, mid, post = layers[:tsp_pos], layers[tsp_pos:tsp_pos + 1], layers[tsp_pos + 1:]
+                g_pre, g_post = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_pre):
+                    run_layers(pre)
+                with torch.cuda.graph(g_post):
+                    run_layers(post)
+                graph = (g_pre, g_post)
+
+                def run():
+                    g_pre.replay()
+                    run_layers(mid)
+                    g_post.replay()
+                run()
+                torch.cuda.synchronize()
+                timed_with = "cuda-graph replay (2 graphs) + eager TSP layer with the NCCL exchange"
         except Exception as e:  # noqa: BLE001
             print(f"[bench] graph capture failed ({type(e).__name__}: {e}); timing eager launches", file=sys.stderr)
             graph = None
+            run = one_step
+            timed_with = "eager C-ABI launches"
             torch.cuda.synchronize()
-    run = graph.replay if graph is not None else one_step
 
     sampler = ClockSampler(local_rank)
     barrier()
@@ -457,7 +485,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, n_prompts),
             "algorithmic_bytes_per_step": int(total_bytes_step),
-            "timed_with": "cuda-graph replay of the C-ABI launches" if graph is not None else "eager C-ABI launches",
+            "timed_with": timed_with,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu, "model": model_extras,
