@@ -118,7 +118,7 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
 
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace || workspace_bytes < 256) return FKV_EWORKSPACE;
-  FKV_CUDA_TRY(cudaMemsetAsync(workspace, 0, 256, (cudaStream_t)stream));
+  FKV_CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
   return FKV_OK;
 }
 

@@ -42,8 +42,8 @@ struct TcArgs {
   int kpos_l, kpos_h, kpos_b, qpos_l, qpos_h, qpos_b;   // coordinate slots of the stride-sorted TMA dims
   int q_heads_per_kv;                                   // model G (query head = kvh * G + g)
   float c;                                              // softmax scale * log2(e)
-  float2* part;                                         // [grid][maxlp][N] pass-1 partial (max, sum)
-  unsigned int* sync_counter;                           // [0] arrivals, [1] departures; zero on entry, left zero on exit
+  unsigned long long* part;                             // [pair][contributor rank][N][2] epoch-tagged (max | sum) words
+  unsigned int* sync_counter;                           // workspace header: [1] departures (left zero), u64 at [2] = launch epoch
   unsigned long long* trace;                            // optional [grid][16] globaltimer stamps (FKV_TC_TRACE=1)
   float* score; int64_t score_sb, score_sh; int out_h0;
 };
@@ -146,6 +146,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// Partial softmax statistics travel between CTAs as two self-validating 64-bit words per row:
+// low half = the fp32 value, high half = a quiet-NaN pattern carrying 22 bits of the launch epoch
+// (44 bits over the two words).  A reader simply re-loads a record until both tags match this launch,
+// so the exchange needs no flag, no fence and no grid-wide barrier: data and "ready" are one word.
+__device__ __forceinline__ unsigned long long tag_word(float v, unsigned int tag) {
+  return (unsigned long long)__float_as_uint(v) | ((unsigned long long)tag << 32);
+}
+__device__ __forceinline__ void st_record(unsigned long long* p, unsigned long long w0, unsigned long long w1) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ld_record(const unsigned long long* p, unsigned long long& w0, unsigned long long& w1) {
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+
 // which CTA owns unit u under the balanced split u0(c) = floor(c * U / grid)
 __device__ __forceinline__ int cta_of_unit(long long u, int U, int grid) { return (int)(((u + 1) * grid - 1) / U); }
 __device__ __forceinline__ int unit_begin(int c, int U, int grid) { return (int)((long long)c * U / grid); }
@@ -216,6 +230,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
   if (threadIdx.x == 64) FKV_TRACE(1);
 
   if (warp == 0) {
@@ -355,6 +370,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     float mn[N], z[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+    // launch epoch (bumped by the last CTA of every launch) -> the two record tags of this launch
+    const unsigned long long epoch = __ldcg(reinterpret_cast<const unsigned long long*>(a.sync_counter + 2)) + 1ull;
+    const unsigned int tag_m = 0x7fc00000u | (unsigned)(epoch & 0x3fffffu);
+    const unsigned int tag_z = 0x7fc00000u | (unsigned)((epoch >> 22) & 0x3fffffu);
 
     int flushed = 0;                                 // local pairs already flushed by this warpgroup
     auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
@@ -402,7 +421,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
           }
           const int pr = pair0 + flushed;
           const int krank = cta - cta_of_unit((long long)pr * a.n_tiles, a.U, grid);
-          a.part[((size_t)pr * a.maxc + krank) * N + et] = make_float2(M, Z);
+          st_record(a.part + (((size_t)pr * a.maxc + krank) * N + et) * 2, tag_word(M, tag_m), tag_word(Z, tag_z));
         }
         named_bar(2, kEpiThreads);
       }
@@ -466,47 +485,39 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     flush_upto(nlp);
     if (et == 0) FKV_TRACE(4);
 
-    // ---------------- grid barrier: every CTA's partials are visible ---------------------------
-    // contributors of each local pair (needs no remote data: computed while others still arrive)
+    // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
+    // No grid barrier: a CTA only needs the partials of the CTAs that share its (b, h) pairs, and every
+    // record says by itself whether it belongs to this launch.
     if (et < nlp) {
       const long long ub = (long long)(pair0 + et) * a.n_tiles;
       ncontrib[et] = cta_of_unit(ub + a.n_tiles - 1, a.U, grid) - cta_of_unit(ub, a.U, grid) + 1;
     }
-    tc_fence_before();
-    if (et == 0) FKV_TRACE(13);
-    named_bar(2, kEpiThreads);                       // every partial of this CTA is ordered before ...
-    if (et == 0) {
-      FKV_TRACE(14);
-      // ... this release-arrive (cumulative at gpu scope); the counter is self-cleaning, see kernel end
-      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.sync_counter) : "memory");
-      unsigned int seen;
-      do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(a.sync_counter) : "memory");
-      } while (seen < (unsigned)grid);
-    }
     named_bar(2, kEpiThreads);
-    tc_fence_after();
-    if (et == 0) FKV_TRACE(5);
-
-    // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
-    named_bar(2, kEpiThreads);
-    // 8 lanes per row; every lane first issues all of its (up to 4) partial loads, then merges.
+    // 8 lanes per row; every lane first issues all of its (up to 4) record loads, then merges.
     for (int idx = et; idx < nlp * N * 8; idx += kEpiThreads) {
       const int sub = idx & 7, n = (idx >> 3) % N, lp = (idx >> 3) / N;
       const int cnt = ncontrib[lp];
-      const float2* src = a.part + ((size_t)(pair0 + lp) * a.maxc) * N + n;
+      const unsigned long long* src = a.part + (((size_t)(pair0 + lp) * a.maxc) * N + n) * 2;
       float M = kEmptyMax, Z = 0.f;
       for (int c0 = sub; c0 < cnt; c0 += 32) {
-        float2 v[4];
+        unsigned long long w0[4], w1[4];
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = c0 + 8 * i;
+            if (c < cnt) ld_record(src + (size_t)c * N * 2, w0[i], w1[i]);
+            else { w0[i] = tag_word(kEmptyMax, tag_m); w1[i] = tag_word(0.f, tag_z); }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ok = ok && ((unsigned)(w0[i] >> 32) == tag_m) && ((unsigned)(w1[i] >> 32) == tag_z);
+        } while (!ok);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int c = c0 + 8 * i;
-          v[i] = (c < cnt) ? __ldcg(src + (size_t)c * N) : make_float2(kEmptyMax, 0.f);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float nm = fmaxf(M, v[i].x);
-          Z = Z * ex2(M - nm) + v[i].y * ex2(v[i].x - nm);
+          const float vm = __uint_as_float((unsigned)w0[i]), vz = __uint_as_float((unsigned)w1[i]);
+          const float nm = fmaxf(M, vm);
+          Z = Z * ex2(M - nm) + vz * ex2(vm - nm);
           M = nm;
         }
       }
@@ -600,10 +611,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
 
   if (threadIdx.x == 64) {
     FKV_TRACE(7);
-    // departure count: the last CTA out resets both counters, so the next launch on this stream
-    // finds them zero again (no memset node in front of every call)
+    // departure count: the last CTA out resets it and advances the epoch, so the next launch on this
+    // stream needs no memset node in front of it and can tell its own records from older ones
     const unsigned int prev = atomicAdd(a.sync_counter + 1, 1u);
-    if (prev == (unsigned)grid - 1) { a.sync_counter[0] = 0u; a.sync_counter[1] = 0u; __threadfence(); }
+    if (prev == (unsigned)grid - 1) {
+      a.sync_counter[1] = 0u;
+      *reinterpret_cast<unsigned long long*>(a.sync_counter + 2) += 1ull;
+      __threadfence();
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -716,7 +731,7 @@ Plan make_plan(const fkv_score_params& p) {
   pl.smem = 1024 + nst * tile_bytes + 2 * q_bytes + misc + 256;
   const int per_min = pl.U / pl.grid;               // every CTA owns at least this many units
   pl.maxc = ceil_div(pl.n_tiles, per_min > 0 ? per_min : 1) + 2;
-  pl.part_bytes = align_up((size_t)p.B * pl.nkv * pl.maxc * pl.N * sizeof(float2), 256);
+  pl.part_bytes = align_up((size_t)p.B * pl.nkv * pl.maxc * pl.N * 2 * sizeof(unsigned long long), 256);
   pl.ok = true;
   return pl;
 }
@@ -733,11 +748,14 @@ int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, i
   cfg.blockDim = dim3(kTcThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: the in-kernel grid barrier is safe
+  cudaLaunchAttribute attr[2];
+  static const char* mode_env = getenv("FKV_TC_LAUNCH");        // experiment switch: coop (default) | both
+  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: CTAs wait on each other's partials
   attr[0].val.cooperative = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (mode_env && mode_env[0] == 'b') ? 2 : 1;
   FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G>, mk, mq, a));
   count_launch();
   return FKV_OK;
@@ -759,7 +777,7 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
   char* ws = reinterpret_cast<char*>(p.workspace);
   a.sync_counter = reinterpret_cast<unsigned int*>(ws);
-  a.part = reinterpret_cast<float2*>(ws + 256);
+  a.part = reinterpret_cast<unsigned long long*>(ws + 256);
   a.score = p.score; a.score_sb = p.score_stride_b; a.score_sh = p.score_stride_h; a.out_h0 = p.h0;
 
   CUtensorMap mk, mq;
