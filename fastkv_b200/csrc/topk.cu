@@ -423,12 +423,57 @@ topk_cluster_kernel(TopkArgs a) {
   csync();
   TK_TRACE(3);
   const uint32_t bin_star = sm.bc[0];
-  const uint32_t n_above = sm.bc[1];
-  const uint32_t n_cand = n_above + sm.bc[2];
+  uint32_t thr = bin_star << 20;                    // candidates are the keys >= thr
+  uint32_t n_above = sm.bc[1];
+  uint32_t n_cand = n_above + sm.bc[2];
   const bool by_value = (a.order == FKV_ORDER_VALUE_DESC);
 
   if (n_cand > (uint32_t)kCandMax) {
-  fallback:
+    // ---- 2b. crowded threshold bin (narrow score distributions put thousands of keys within one
+    // 1/8-octave bin): split bin* by the next 12 key bits, same cluster histogram once more --------
+    for (int i = tid; i < kMaxBins; i += kThreads) { sm.hist[i] = 0; sm.ghist[i] = 0; }
+    csync();                                        // the leader's ghist is zero before anybody adds to it
+    for (int i = tid; i < cnt; i += kThreads) {
+      const uint32_t key = sm.keys[key_slot(i)];
+      if ((key >> 20) == bin_star) atomicAdd(&sm.hist[(key >> 8) & 0xfffu], 1u);
+    }
+    __syncthreads();
+    if (multi) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t c = sm.hist[tid * 4 + i];
+        if (c) atomicAdd(&lead.ghist[tid * 4 + i], c);
+      }
+      cluster.sync();
+    }
+    if (crank == 0) {
+      const uint32_t* gh = multi ? sm.ghist : sm.hist;
+      const uint32_t kk = (uint32_t)k - n_above;    // still needed from inside bin*
+      uint32_t local[4], ls = 0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { local[i] = gh[kMaxBins - 1 - (tid * 4 + i)]; ls += local[i]; }
+      uint32_t total;
+      const uint32_t incl = block_scan_incl(ls, sm.wsum, total);
+      uint32_t above = incl - ls;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (above < kk && kk <= above + local[i]) {
+          const uint32_t sub = (uint32_t)(kMaxBins - 1 - (tid * 4 + i));
+          for (int c = 0; c < C; ++c) {
+            uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, c) : sm.bc;
+            rbc[7] = (bin_star << 20) | (sub << 8); rbc[1] = n_above + above; rbc[2] = local[i];
+          }
+        }
+        above += local[i];
+      }
+    }
+    csync();
+    thr = sm.bc[7];
+    n_above = sm.bc[1];
+    n_cand = n_above + sm.bc[2];
+  }
+
+  if (n_cand > (uint32_t)kCandMax) {
     // heavy ties / very flat rows: the leader re-selects from global memory with the generic path
     if (a.write_dense) __threadfence();
     csync();                                        // dense row (if any) fully written, remote smem no longer needed
@@ -456,7 +501,7 @@ topk_cluster_kernel(TopkArgs a) {
   // ---- 3. send candidates (bin >= bin*) to the leader: count, one cursor atomic per warp, write ------
   {
     uint32_t mine = 0;
-    for (int i = tid; i < cnt; i += kThreads) mine += ((sm.keys[key_slot(i)] >> 20) >= bin_star);
+    for (int i = tid; i < cnt; i += kThreads) mine += (sm.keys[key_slot(i)] >= thr);
     uint32_t pre = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -470,7 +515,7 @@ topk_cluster_kernel(TopkArgs a) {
     uint32_t pos = wbase + pre - mine;
     for (int i = tid; i < cnt; i += kThreads) {
       const uint32_t key = sm.keys[key_slot(i)];
-      if ((key >> 20) >= bin_star)
+      if (key >= thr)
         lead.cand[pos++] = ((unsigned long long)key << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
     }
   }
@@ -486,7 +531,7 @@ topk_cluster_kernel(TopkArgs a) {
     uint32_t* cursor = sm.hist;
     uint16_t* bbase = sm.bbase;
     unsigned long long* grouped = sm.sortbuf;
-    const uint32_t klo = bin_star << 20;
+    const uint32_t klo = thr;
     const uint32_t khi = (sm.bc[6] << 20) | 0xfffffu;                   // upper bound of the top non-empty 12-bit bin
     const unsigned long long range = (unsigned long long)(khi - klo) + 1ull;
     const unsigned long long mult = (((unsigned long long)kMaxBins << 32) - 1ull) / range;   // bin = ((key-klo)*mult) >> 32 < 4096
@@ -598,7 +643,7 @@ topk_cluster_kernel(TopkArgs a) {
   }
 
   // ---- 5. INDEX_ASC: every CTA compacts its own selected keys in index order ---------------------------
-  const unsigned long long thr = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
+  const unsigned long long kth_c = ((unsigned long long)sm.bc[5] << 32) | sm.bc[4];
   constexpr int kPerThread = kSliceKeys / kThreads;               // 16 consecutive keys per thread
   uint32_t mine = 0;
   uint32_t selmask = 0;
@@ -607,7 +652,7 @@ topk_cluster_kernel(TopkArgs a) {
     const int i = tid * kPerThread + e;
     if (i < cnt) {
       const unsigned long long c = ((unsigned long long)sm.keys[key_slot(i)] << 32) | (uint32_t)(0xffffffffu - (uint32_t)(base + i));
-      if (c >= thr) { ++mine; selmask |= 1u << e; }
+      if (c >= kth_c) { ++mine; selmask |= 1u << e; }
     }
   }
   uint32_t cta_total;

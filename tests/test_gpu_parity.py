@@ -281,6 +281,9 @@ def test_topk_kernel_is_exact(n, k):
         torch.randint(0, 5, (n,), generator=g).float(),                # heavy exact ties
         torch.zeros(n),                                                # all equal
         torch.rand(n, generator=g).pow(8) * 1e-6,                      # tiny positive (softmax-like)
+        1.0 + 0.01 * torch.rand(n, generator=g),                       # narrow: one crowded 12-bit bin (refinement pass)
+        1.0 + 1e-5 * torch.rand(n, generator=g),                       # very narrow: crowded after refinement too
+        (3e-5 * (1.0 + 0.05 * torch.randn(n, generator=g))).abs(),     # pooled-score-like: tight bell around a tiny mean
     ])
     rows[1, ::97] = -0.0
     got = ops.topk(rows.to(DEV), k, order=L.ORDER_VALUE_DESC).cpu()
