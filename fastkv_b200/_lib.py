@@ -224,3 +224,13 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
         check(load().fkv_workspace_init(buf.data_ptr(), buf.numel(), torch.cuda.current_stream(device).cuda_stream))
         _workspaces[key] = buf
     return buf
+
+
+WS_HEADER = 256   # fkv_score / fkv_compress keep the scoring kernel's departure counter + launch epoch here
+
+
+def scratch(device: torch.device, nbytes: int):
+    """(ptr, bytes) of the shared buffer PAST the scoring header, for entry points that use their
+    workspace as plain scratch (fkv_topk, fkv_decode_attn): they must not overwrite that header."""
+    buf = workspace(device, nbytes + WS_HEADER)
+    return buf.data_ptr() + WS_HEADER, buf.numel() - WS_HEADER

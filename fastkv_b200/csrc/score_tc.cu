@@ -33,12 +33,14 @@ constexpr int kEpiWarps = 4 * kNumWG;
 constexpr int kTcThreads = 64 + kEpiThreads;
 constexpr int kMaxLocalPairs = 8;
 constexpr int kMaxStages = 6;
+constexpr int kMaxPhases = 512;            // (b, h) pairs are processed in groups whose logits fit in TMEM
 constexpr float kLazyTau = 6.0f;          // log2 units of headroom before a running max is raised
 constexpr float kEmptyMax = -1.0e30f;     // "no key seen yet" (finite, so exp2(x - m) never sees inf - inf)
 
 struct TcArgs {
   int B, L, P, D, nkv, kv0, n_tiles, S, half, ks, pooling, group_sum, is_f16;
   int U, maxlp, nst, maxc;
+  int npairs, ppp, nph;                                 // (b, h) pairs, pairs per phase, phases
   int kpos_l, kpos_h, kpos_b, qpos_l, qpos_h, qpos_b;   // coordinate slots of the stride-sorted TMA dims
   int q_heads_per_kv;                                   // model G (query head = kvh * G + g)
   float c;                                              // softmax scale * log2(e)
@@ -160,9 +162,10 @@ __device__ __forceinline__ void ld_record(const unsigned long long* p, unsigned 
   asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
 }
 
-// which CTA owns unit u under the balanced split u0(c) = floor(c * U / grid)
-__device__ __forceinline__ int cta_of_unit(long long u, int U, int grid) { return (int)(((u + 1) * grid - 1) / U); }
-__device__ __forceinline__ int unit_begin(int c, int U, int grid) { return (int)((long long)c * U / grid); }
+// balanced split of U units over the grid: u0(c) = floor(c * U / grid); with fewer units than CTAs the
+// first U CTAs take one unit each, so the CTAs that share a (b, h) pair are always consecutive and non-empty
+__device__ __forceinline__ int unit_begin(int c, int U, int grid) { return U >= grid ? (int)((long long)c * U / grid) : min(c, U); }
+__device__ __forceinline__ int cta_of_unit(long long u, int U, int grid) { return U >= grid ? (int)(((u + 1) * grid - 1) / U) : (int)u; }
 
 template <int W, int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -183,12 +186,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   const uint32_t k_off = 0;
   const uint32_t q_off = k_off + a.nst * tile_bytes;
   const uint32_t misc_off = q_off + 2 * ((q_bytes + 1023) & ~1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);   // full[6] empty[6] qfull[2] qempty[2] tfull[32] tempty[32] rdone[32]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 112);
-  float2* stage = reinterpret_cast<float2*>(tmem_slot + 4);             // [8][N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + misc_off);   // full[6] empty[6] qfull[2] qempty[2] tfull[32] tempty[32]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 80);
+  float2* stage = reinterpret_cast<float2*>(tmem_slot + 4);             // [epilogue warps][N]
   float2* colstat = stage + kEpiWarps * N;                              // [maxlp][N]
   float* vbuf = reinterpret_cast<float*>(colstat + kMaxLocalPairs * N); // [wg][2 buf][G][128]
   int* ncontrib = reinterpret_cast<int*>(vbuf + kNumWG * 2 * G * kTile);     // [maxlp] CTAs contributing to each local pair
+  int* ph_u0 = ncontrib + kMaxLocalPairs;                               // [nph] first unit of this CTA's slice of the phase
+  int* ph_T = ph_u0 + kMaxPhases;                                       // [nph] tiles of this CTA in the phase
 
   auto bar_full = [&](int s) { return smem_u32(bars + s); };
   auto bar_empty = [&](int s) { return smem_u32(bars + 6 + s); };
@@ -196,26 +201,24 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   auto bar_qempty = [&](int s) { return smem_u32(bars + 14 + s); };
   auto bar_tfull = [&](int s) { return smem_u32(bars + 16 + s); };
   auto bar_tempty = [&](int s) { return smem_u32(bars + 48 + s); };
-  auto bar_rdone = [&](int s) { return smem_u32(bars + 80 + s); };   // resident tile re-read in pass 2
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grid = gridDim.x, cta = blockIdx.x;
-  const int u0 = unit_begin(cta, a.U, grid), u1 = unit_begin(cta + 1, a.U, grid);
-  const int T = u1 - u0;                              // tiles of this CTA (>= 1: grid <= U)
-  const int pair0 = u0 / a.n_tiles;
-  const int nlp = (u1 - 1) / a.n_tiles - pair0 + 1;   // local (b, h) pairs touched
-  // MMA jobs: pass 1 computes every tile (ascending) into TMEM block tile % NB; the last
-  // min(T, NB) tiles therefore stay resident and pass 2 only recomputes tiles T-NB-1 .. 0.
-  const int n_refill = T > NB ? T - NB : 0;
-  const int n_mma_jobs = T + n_refill;
-  auto mma_job_tile = [&](int m) { return m < T ? m : (T - NB - 1 - (m - T)); };
-  // fills of block b during pass 1
-  auto fills_pass1 = [&](int b) { return (T - 1 - b) / NB + 1; };
+  const int nph = a.nph;
+  // Phase ph covers the (b, h) pairs [ph * ppp, ...); its tiles are split evenly over the grid, at most
+  // NB per CTA, so a tile's logits stay in TMEM between its two passes and K is read exactly once.
+  for (int ph = threadIdx.x; ph < nph; ph += kTcThreads) {
+    const int p0 = ph * a.ppp;
+    const int Uph = min(a.ppp, a.npairs - p0) * a.n_tiles;
+    const int r0 = unit_begin(cta, Uph, grid), r1 = unit_begin(cta + 1, Uph, grid);
+    ph_u0[ph] = p0 * a.n_tiles + r0;
+    ph_T[ph] = r1 - r0;
+  }
 
-  if (warp == 0) {                                  // 112 barriers, a few per lane
+  if (warp == 0) {                                  // 80 barriers, a few per lane
     for (int s = lane; s < kMaxStages; s += 32) { mbar_init(bar_full(s), 1); mbar_init(bar_empty(s), 1); }
     if (lane < 2) { mbar_init(bar_qfull(lane), 1); mbar_init(bar_qempty(lane), 1); }
-    for (int s = lane; s < NB; s += 32) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128); mbar_init(bar_rdone(s), 128); }
+    for (int s = lane; s < NB; s += 32) { mbar_init(bar_tfull(s), 1); mbar_init(bar_tempty(s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -238,7 +241,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // One thread; everything in the loop is incremental (no divisions, no local arrays): at
     // ~5 cycles per dependent instruction a fat loop body would pace the whole pipeline.
     if (lane == 0) {
-      // coordinate slot k of the stride-sorted tensor map receives row / head / batch
       const int kl1 = a.kpos_l == 1, kl2 = a.kpos_l == 2, kl3 = a.kpos_l == 3;
       const int kh1 = a.kpos_h == 1, kh2 = a.kpos_h == 2, kh3 = a.kpos_h == 3;
       const int kb1 = a.kpos_b == 1, kb2 = a.kpos_b == 2, kb3 = a.kpos_b == 3;
@@ -247,46 +249,45 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       const int qb1 = a.qpos_b == 1, qb2 = a.qpos_b == 2, qb3 = a.qpos_b == 3;
       const int slabs = a.D >> 6;
       int cur_pair = -1, qu = -1;
-      int pair = pair0, t = u0 - pair0 * a.n_tiles;  // cursor of the next tile to load
       int hb1 = 0, hb2 = 0, hb3 = 0;                 // head/batch part of the K coordinates
       int slot = 0, ephase = 1;                      // ring slot + parity for the empty-barrier wait
-      for (int m = 0; m < n_mma_jobs; ++m) {
-        if (m == T) {                                // pass-2 refills restart at tile T-NB-1, descending
-          const int u = u0 + T - NB - 1;
-          pair = u / a.n_tiles; t = u - pair * a.n_tiles;
-        }
-        const bool new_pair = (pair != cur_pair);
-        int pb = 0, pkvh = 0;
-        if (new_pair) {
-          cur_pair = pair; ++qu;
-          pb = pair / a.nkv; pkvh = a.kv0 + pair - pb * a.nkv;
-          hb1 = pkvh * kh1 + pb * kb1; hb2 = pkvh * kh2 + pb * kb2; hb3 = pkvh * kh3 + pb * kb3;
-        }
-        if (m >= a.nst) mbar_wait(bar_empty(slot), ephase);
-        FKV_TRACE2(0, m);
-        mbar_expect_tx(bar_full(slot), tile_bytes);
-        const uint32_t kdst = base + k_off + slot * tile_bytes;
-        const int row0 = t * a.S - a.half;           // may be negative / run past L: TMA zero-fills
-        const int c1 = row0 * kl1 + hb1, c2 = row0 * kl2 + hb2, c3 = row0 * kl3 + hb3;
-        tma_load_4d(kdst, &tm_k, bar_full(slot), 0, c1, c2, c3);
-        if (slabs == 2) tma_load_4d(kdst + kTile * 128, &tm_k, bar_full(slot), 64, c1, c2, c3);
-        if (new_pair) {                              // new (b, h): stage its N query rows (B operand) after the K tile
-          const int qb = qu & 1;
-          if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
-          mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
-          const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
-          for (int slab = 0; slab < slabs; ++slab)
+      int m = 0;                                     // tiles issued so far
+      for (int ph = 0; ph < nph; ++ph) {
+        const int T = ph_T[ph];
+        if (T == 0) continue;
+        int pair = ph_u0[ph] / a.n_tiles, t = ph_u0[ph] - pair * a.n_tiles;
+        for (int i = 0; i < T; ++i, ++m) {
+          const bool new_pair = (pair != cur_pair);
+          int pb = 0, pkvh = 0;
+          if (new_pair) {
+            cur_pair = pair; ++qu;
+            pb = pair / a.nkv; pkvh = a.kv0 + pair - pb * a.nkv;
+            hb1 = pkvh * kh1 + pb * kb1; hb2 = pkvh * kh2 + pb * kb2; hb3 = pkvh * kh3 + pb * kb3;
+          }
+          if (m >= a.nst) mbar_wait(bar_empty(slot), ephase);
+          FKV_TRACE2(0, m);
+          mbar_expect_tx(bar_full(slot), tile_bytes);
+          const uint32_t kdst = base + k_off + slot * tile_bytes;
+          const int row0 = t * a.S - a.half;         // may be negative / run past L: TMA zero-fills
+          const int c1 = row0 * kl1 + hb1, c2 = row0 * kl2 + hb2, c3 = row0 * kl3 + hb3;
+          tma_load_4d(kdst, &tm_k, bar_full(slot), 0, c1, c2, c3);
+          if (slabs == 2) tma_load_4d(kdst + kTile * 128, &tm_k, bar_full(slot), 64, c1, c2, c3);
+          if (new_pair) {                            // new (b, h): stage its N query rows (B operand) after the K tile
+            const int qb = qu & 1;
+            if (qu >= 2) mbar_wait(bar_qempty(qb), ((qu >> 1) - 1) & 1);
+            mbar_expect_tx(bar_qfull(qb), N * a.D * 2);
+            const uint32_t qdst = base + q_off + qb * ((q_bytes + 1023) & ~1023);
+            for (int slab = 0; slab < slabs; ++slab)
 #pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const int hq = pkvh * a.q_heads_per_kv + g;
-              tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
-                          a.P * ql1 + hq * qh1 + pb * qb1, a.P * ql2 + hq * qh2 + pb * qb2, a.P * ql3 + hq * qh3 + pb * qb3);
-            }
+              for (int g = 0; g < G; ++g) {
+                const int hq = pkvh * a.q_heads_per_kv + g;
+                tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
+                            a.P * ql1 + hq * qh1 + pb * qb1, a.P * ql2 + hq * qh2 + pb * qb2, a.P * ql3 + hq * qh3 + pb * qb3);
+              }
+          }
+          if (++slot == a.nst) { slot = 0; ephase ^= 1; }
+          if (++t == a.n_tiles) { t = 0; ++pair; }
         }
-        if (m == T - 1) FKV_TRACE(10);
-        if (++slot == a.nst) { slot = 0; ephase ^= 1; }
-        if (m < T) { if (++t == a.n_tiles) { t = 0; ++pair; } }
-        else       { if (--t < 0) { t = a.n_tiles - 1; --pair; } }
       }
     }
   } else if (warp == 1) {
@@ -297,64 +298,46 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       const uint64_t desc_hi = (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
       const bool two_slabs = (a.D == 128);
       int cur_pair = -1, qu = -1;
-      int pair = pair0, t = u0 - pair0 * a.n_tiles;
-      int lt = 0;
       int slot = 0, fphase = 0;
       uint32_t qa = 0;
-      for (int m = 0; m < n_mma_jobs; ++m) {
-        if (m == T) {
-          lt = T - NB - 1;
-          const int u = u0 + lt;
-          pair = u / a.n_tiles; t = u - pair * a.n_tiles;
-        }
-        if (pair != cur_pair) {
-          cur_pair = pair; ++qu;
-          mbar_wait(bar_qfull(qu & 1), (qu >> 1) & 1);
-          qa = base + q_off + (qu & 1) * ((q_bytes + 1023) & ~1023);
-        }
-        const int blk = lt & (NB - 1);
-        mbar_wait(bar_full(slot), fphase);
-        FKV_TRACE2(1, m);
-        // The block must have been drained by the epilogue.  tempty[blk] completes one phase per
-        // consumed FILL, so "fill f may start" == "phase f-1 complete" and the waiter is never more
-        // than one phase behind (parity waits cannot express a longer lag).  The pass-2 re-read of
-        // the tile left resident by pass 1 is tracked by its own single-phase barrier rdone[blk].
-        {
-          int fill;
-          if (m < T) fill = lt / NB;
-          else {
-            const int n1 = fills_pass1(blk);
-            fill = 2 * n1 - 2 - lt / NB;                           // n1 + (n1 - 2 - lt/NB)
-            if (fill == n1) mbar_wait(bar_rdone(blk), 0);
+      int m = 0;
+      for (int ph = 0; ph < nph; ++ph) {
+        const int T = ph_T[ph];
+        if (T == 0) continue;
+        int pair = ph_u0[ph] / a.n_tiles, t = ph_u0[ph] - pair * a.n_tiles;
+        for (int i = 0; i < T; ++i, ++m) {
+          if (pair != cur_pair) {
+            if (qu >= 0) umma_commit(bar_qempty(qu & 1));        // the previous pair's Q buffer is free once its MMAs retire
+            cur_pair = pair; ++qu;
+            mbar_wait(bar_qfull(qu & 1), (qu >> 1) & 1);
+            qa = base + q_off + (qu & 1) * ((q_bytes + 1023) & ~1023);
           }
-          if (fill >= 1) mbar_wait(bar_tempty(blk), (fill - 1) & 1);
-        }
-        tc_fence_after();
-        const uint32_t ka = base + k_off + slot * tile_bytes;
-        const uint32_t d_tmem = tmem_base + blk * NMMA;
-        const uint64_t ad0 = desc_hi | (uint64_t)((ka & 0x3ffffu) >> 4);
-        const uint64_t bd0 = desc_hi | (uint64_t)((qa & 0x3ffffu) >> 4);
-        // K advances 16 elements = 32 B (encoded +2) inside the 128B swizzle atom; the second
-        // 64-wide slab of D starts one full operand slab later
+          const int blk = m & (NB - 1);
+          mbar_wait(bar_full(slot), fphase);
+          FKV_TRACE2(1, m);
+          // the block is free once the tile that used it before (m - NB) went through its SECOND pass;
+          // tempty[blk] completes one phase per such read, so the waiter is never more than one phase behind
+          if (m >= NB) mbar_wait(bar_tempty(blk), ((m / NB) - 1) & 1);
+          tc_fence_after();
+          const uint32_t ka = base + k_off + slot * tile_bytes;
+          const uint32_t d_tmem = tmem_base + blk * NMMA;
+          const uint64_t ad0 = desc_hi | (uint64_t)((ka & 0x3ffffu) >> 4);
+          const uint64_t bd0 = desc_hi | (uint64_t)((qa & 0x3ffffu) >> 4);
+          // K advances 16 elements = 32 B (encoded +2) inside the 128B swizzle atom; the second
+          // 64-wide slab of D starts one full operand slab later
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, k > 0 ? 1u : 0u);
-        if (two_slabs) {
+          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad0 + 2 * k, bd0 + 2 * k, idesc, k > 0 ? 1u : 0u);
+          if (two_slabs) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d_tmem, ad0 + ((kTile * 128) >> 4) + 2 * k, bd0 + ((NMMA * 128) >> 4) + 2 * k, idesc, 1u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem, ad0 + ((kTile * 128) >> 4) + 2 * k, bd0 + ((NMMA * 128) >> 4) + 2 * k, idesc, 1u);
+          }
+          umma_commit(bar_empty(slot));              // smem slot reusable once these MMAs retire
+          umma_commit(bar_tfull(blk));               // accumulator ready for the epilogue
+          FKV_TRACE2(2, m);
+          if (++slot == a.nst) { slot = 0; fphase ^= 1; }
+          if (++t == a.n_tiles) { t = 0; ++pair; }
         }
-        umma_commit(bar_empty(slot));                // smem slot reusable once these MMAs retire
-        umma_commit(bar_tfull(blk));                 // accumulator ready for the epilogue
-        if (m == T - 1) FKV_TRACE(9);
-        FKV_TRACE2(2, m);
-        if (++slot == a.nst) { slot = 0; fphase ^= 1; }
-        // advance the cursor; release the Q buffer after the last tile of a pair
-        int npair = pair;
-        if (m < T) { ++lt; if (++t == a.n_tiles) { t = 0; ++npair; } }
-        else       { --lt; if (--t < 0) { t = a.n_tiles - 1; --npair; } }
-        if (m == T - 1 && n_refill > 0) npair = (u0 + T - NB - 1) / a.n_tiles;   // the cursor jumps there next
-        if (m + 1 == n_mma_jobs || npair != pair) umma_commit(bar_qempty(qu & 1));
-        pair = npair;
       }
     }
   } else {
@@ -375,6 +358,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     const unsigned int tag_m = 0x7fc00000u | (unsigned)(epoch & 0x3fffffu);
     const unsigned int tag_z = 0x7fc00000u | (unsigned)((epoch >> 22) & 0x3fffffu);
 
+    const float pad = (a.pooling == FKV_POOL_MAX) ? -INFINITY : 0.f;
+    const float inv_ks = 1.0f / (float)a.ks;
+    int jbase = 0;                                   // CTA-wide index of the phase's first tile (TMEM block = index % NB)
+    int vcount = 0;                                  // pass-2 tiles done by this warpgroup (vote double buffer)
+    for (int ph = 0; ph < nph; ++ph) {
+    const int T = ph_T[ph];                          // tiles of this CTA in the phase (<= NB)
+    if (T == 0) continue;                            // uniform over the CTA
+    const int u0 = ph_u0[ph];
+    const int pair0 = u0 / a.n_tiles;
+    const int nlp = (u0 + T - 1) / a.n_tiles - pair0 + 1;   // local (b, h) pairs touched
+    const int p0 = ph * a.ppp;                       // first pair of the phase
+    const int Uph = min(a.ppp, a.npairs - p0) * a.n_tiles;
+#pragma unroll
+    for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
     int flushed = 0;                                 // local pairs already flushed by this warpgroup
     auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
       for (; flushed < lp_end; ++flushed) {
@@ -406,9 +403,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         }
 #pragma unroll
         for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
-        if (et == 0) FKV_TRACE(11);
         named_bar(2, kEpiThreads);
-        if (et == 0) FKV_TRACE(12);
         if (et < N) {
           float M = kEmptyMax;
 #pragma unroll
@@ -420,7 +415,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             Z += v.y * ex2(v.x - M);
           }
           const int pr = pair0 + flushed;
-          const int krank = cta - cta_of_unit((long long)pr * a.n_tiles, a.U, grid);
+          const int krank = cta - cta_of_unit((long long)(pr - p0) * a.n_tiles, Uph, grid);
           st_record(a.part + (((size_t)pr * a.maxc + krank) * N + et) * 2, tag_word(M, tag_m), tag_word(Z, tag_z));
         }
         named_bar(2, kEpiThreads);
@@ -431,17 +426,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     int pair, t;
     { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
     for (int j = wg; j < T; j += kNumWG) {
-      const int blk = j & (NB - 1);
+      const int blk = (jbase + j) & (NB - 1);
       flush_upto(pair - pair0);
-      mbar_wait(bar_tfull(blk), (j / NB) & 1);
-      if (et == 0 && j == 0) FKV_TRACE(2);
-      if ((et & 127) == 0) FKV_TRACE2(3, j);
+      mbar_wait(bar_tfull(blk), ((jbase + j) / NB) & 1);
+      if (et == 0 && jbase + j == 0) FKV_TRACE(2);
       tc_fence_after();
       float s[N];
       tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
-      tc_fence_before();
-      mbar_arrive(bar_tempty(blk));
       const int key = t * a.S - a.half + row;
       const bool own = (row >= a.half) && (row < a.half + a.S) && (key < a.L);
       const bool has_window = (t * a.S - a.half + kTile > a.P);   // warp-uniform
@@ -481,16 +473,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
-    if (et == 0) FKV_TRACE(3);
+    if (et == 0 && ph == nph - 1) FKV_TRACE(3);
     flush_upto(nlp);
-    if (et == 0) FKV_TRACE(4);
+    if (et == 0 && ph == nph - 1) FKV_TRACE(4);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
     // No grid barrier: a CTA only needs the partials of the CTAs that share its (b, h) pairs, and every
     // record says by itself whether it belongs to this launch.
     if (et < nlp) {
-      const long long ub = (long long)(pair0 + et) * a.n_tiles;
-      ncontrib[et] = cta_of_unit(ub + a.n_tiles - 1, a.U, grid) - cta_of_unit(ub, a.U, grid) + 1;
+      const long long ub = (long long)(pair0 + et - p0) * a.n_tiles;
+      ncontrib[et] = cta_of_unit(ub + a.n_tiles - 1, Uph, grid) - cta_of_unit(ub, Uph, grid) + 1;
     }
     named_bar(2, kEpiThreads);
     // 8 lanes per row; every lane first issues all of its (up to 4) record loads, then merges.
@@ -531,39 +523,29 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       if (sub == 0) colstat[lp * N + n] = make_float2(M, 1.0f / Z);
     }
     named_bar(2, kEpiThreads);
-    if (et == 0) FKV_TRACE(6);
+    if (et == 0 && ph == nph - 1) FKV_TRACE(6);
 
     // ---------------- pass 2: votes -> pool -> group sum -> score ------------------------------
-    // tiles in descending order; the first min(T, NB) of them are still resident in TMEM
-    const float pad = (a.pooling == FKV_POOL_MAX) ? -INFINITY : 0.f;
-    const float inv_ks = 1.0f / (float)a.ks;
+    // every tile of the phase is still resident in TMEM; reading it frees the block for the next phase
     int cur_lp = -1, b = 0, kvl = 0;
-    { const int u = u0 + T - 1 - wg; pair = u >= 0 ? u / a.n_tiles : 0; t = u - pair * a.n_tiles; }
+    { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
     for (int j2 = wg; j2 < T; j2 += kNumWG) {
-      const int lt = T - 1 - j2;
       const int lp = pair - pair0;
-      const int blk = lt & (NB - 1);
+      const int blk = (jbase + j2) & (NB - 1);
       if (lp != cur_lp) {                            // (max, 1/sum) of this pair's rows -> registers
         cur_lp = lp;
         b = pair / a.nkv; kvl = pair - b * a.nkv;
 #pragma unroll
         for (int n = 0; n < N; ++n) { const float2 v = colstat[lp * N + n]; mn[n] = v.x; z[n] = v.y; }
       }
-      if (j2 >= NB) {                                // recomputed tile: wait for its MMA
-        const int fill = 2 * fills_pass1(blk) - 2 - lt / NB;
-        mbar_wait(bar_tfull(blk), fill & 1);
-      }
-      tc_fence_after();
-      if (et == 0) FKV_TRACE2(4, j2 / kNumWG);
       float s[N];
       tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
-      if (et == 0) FKV_TRACE2(5, j2 / kNumWG);
       tc_fence_before();
-      mbar_arrive(j2 >= NB ? bar_tempty(blk) : bar_rdone(blk));
+      mbar_arrive(bar_tempty(blk));
       const int key = t * a.S - a.half + row;
       const bool in_prefix = (key >= 0) && (key < a.P);
-      float* vb = vbuf + ((wg * 2 + ((j2 / kNumWG) & 1)) * G) * kTile;
+      float* vb = vbuf + ((wg * 2 + (vcount++ & 1)) * G) * kTile;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         float vote = 0.f;
@@ -572,9 +554,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
           vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mn[g * W + r])), z[g * W + r], vote);
         vb[g * kTile + row] = in_prefix ? vote : pad;
       }
-      if (et == 0) FKV_TRACE2(6, j2 / kNumWG);
       named_bar(3 + wg, 128);
-      if (et == 0) FKV_TRACE2(7, j2 / kNumWG);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
       if (own) {
         float acc = 0.f;
@@ -603,10 +583,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         }
         if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
       }
-      if (et == 0) FKV_TRACE2(8, j2 / kNumWG);
-      t -= kNumWG;
-      while (t < 0) { t += a.n_tiles; --pair; }
+      t += kNumWG;
+      while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
+    jbase += T;
+    }                                                // phases
   }
 
   if (threadIdx.x == 64) {
@@ -689,7 +670,7 @@ int make_map(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int 
 }
 
 struct Plan {
-  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst, maxc;
+  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst, maxc, npairs, ppp, nph;
   size_t smem, part_bytes;
   bool ok;
 };
@@ -716,22 +697,38 @@ Plan make_plan(const fkv_score_params& p) {
   if (U > (1ll << 30)) return pl;
   pl.U = (int)U;
   pl.grid = (int)(U < num_sms() ? U : num_sms());
-  const int per = ceil_div(pl.U, pl.grid);
-  pl.maxlp = ceil_div(per, pl.n_tiles) + 1;
-  if (pl.maxlp > kMaxLocalPairs) return pl;
+  // phases: groups of `ppp` (b, h) pairs whose tiles fit in the TMEM blocks of the CTAs (<= NB tiles per
+  // CTA and phase), so every tile's logits stay on chip between the two passes
+  pl.npairs = p.B * pl.nkv;
+  {
+    const int NBk = 512 / (pl.N < 16 ? 16 : pl.N);
+    long long cap_tiles = NBk;                                           // per CTA and phase
+    if ((long long)(kMaxLocalPairs - 1) * pl.n_tiles < cap_tiles) cap_tiles = (long long)(kMaxLocalPairs - 1) * pl.n_tiles;
+    static const int env_ppp = getenv("FKV_TC_PPP") ? atoi(getenv("FKV_TC_PPP")) : 0;
+    int ppp = 1;
+    while (ppp < pl.npairs && ceil_div((long long)(ppp + 1) * pl.n_tiles, pl.grid) <= cap_tiles) ++ppp;
+    if (env_ppp > 0 && env_ppp < ppp) ppp = env_ppp;                     // experiments: smaller phases
+    if (ceil_div((long long)ppp * pl.n_tiles, pl.grid) > NBk) return pl; // one pair alone overflows TMEM (~290k tokens at N = 32)
+    pl.nph = ceil_div(pl.npairs, ppp);
+    if (pl.nph > kMaxPhases) return pl;
+    pl.ppp = ceil_div(pl.npairs, pl.nph);                                // same phase count, balanced sizes
+    const int t_ph = (int)ceil_div((long long)pl.ppp * pl.n_tiles, pl.grid);
+    pl.maxlp = ceil_div(t_ph, pl.n_tiles) + 1;
+    if (pl.maxlp > kMaxLocalPairs) return pl;
+  }
   const int NMMA = pl.N < 16 ? 16 : pl.N;
   const size_t tile_bytes = (size_t)kTile * p.D * 2;
   const size_t q_bytes = ((size_t)NMMA * p.D * 2 + 1023) & ~(size_t)1023;
-  const size_t misc = 112 * 8 + 16 + (size_t)kEpiWarps * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)kNumWG * 2 * pl.G * kTile * 4 + kMaxLocalPairs * 4;
+  const size_t misc = 80 * 8 + 16 + (size_t)kEpiWarps * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)kNumWG * 2 * pl.G * kTile * 4 +
+                      kMaxLocalPairs * 4 + 2 * kMaxPhases * 4;
   const size_t budget = 227 * 1024 - 1024 - 2 * q_bytes - misc - 256;
   int nst = (int)(budget / tile_bytes);
   if (nst > kMaxStages) nst = kMaxStages;
   if (nst < 2) return pl;
   pl.nst = nst;
   pl.smem = 1024 + nst * tile_bytes + 2 * q_bytes + misc + 256;
-  const int per_min = pl.U / pl.grid;               // every CTA owns at least this many units
-  pl.maxc = ceil_div(pl.n_tiles, per_min > 0 ? per_min : 1) + 2;
-  pl.part_bytes = align_up((size_t)p.B * pl.nkv * pl.maxc * pl.N * 2 * sizeof(unsigned long long), 256);
+  pl.maxc = pl.n_tiles < pl.grid ? pl.n_tiles : pl.grid;   // CTAs that can contribute to one pair
+  pl.part_bytes = align_up((size_t)pl.npairs * pl.maxc * pl.N * 2 * sizeof(unsigned long long), 256);
   pl.ok = true;
   return pl;
 }
@@ -774,6 +771,7 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
   a.pooling = p.pooling; a.group_sum = (p.mode == FKV_MODE_FASTKV); a.is_f16 = (p.dtype == FKV_F16);
   a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.maxc = pl.maxc; a.q_heads_per_kv = pl.G;
+  a.npairs = pl.npairs; a.ppp = pl.ppp; a.nph = pl.nph;
   a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
   char* ws = reinterpret_cast<char*>(p.workspace);
   a.sync_counter = reinterpret_cast<unsigned int*>(ws);
@@ -805,15 +803,13 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
     cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost);
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < pl.grid; ++c) if (host[c * 16] < t0) t0 = host[c * 16];
-    const char* names[15] = {"start", "setup", "first_acc", "pass1_end", "flushed", "grid_bar", "colstat", "pass2_end", "exit", "mma_p1_end", "tma_p1_end", "fl_shfl", "fl_bar1", "gb_fence", "gb_bar1"};
-    for (int sidx = 0; sidx < 15; ++sidx) {
+    const char* names[9] = {"start", "setup", "first_acc", "last_p1_end", "last_flushed", "-", "last_colstat", "pass2_end", "exit"};
+    fprintf(stderr, "[fkv trace] L=%d grid=%d pairs=%d ppp=%d phases=%d tiles/pair=%d stages=%d\n", p.L, pl.grid, pl.npairs, pl.ppp, pl.nph, pl.n_tiles, pl.nst);
+    for (int sidx = 0; sidx < 9; ++sidx) {
+      if (sidx == 5) continue;
       unsigned long long mn = ~0ull, mx = 0; double avg = 0;
       for (int c = 0; c < pl.grid; ++c) { unsigned long long v = host[c * 16 + sidx] - t0; if (v < mn) mn = v; if (v > mx) mx = v; avg += v; }
-      if (sidx == 0) for (int m = 0; m < 16; ++m) fprintf(stderr, "[fkv tile %2d] tma_issue %7.2f  mma_full %7.2f  mma_commit %7.2f  epi_tfull %7.2f\n", m,
-          (host[4096 + m] - t0) / 1e3, (host[4096 + 64 + m] - t0) / 1e3, (host[4096 + 128 + m] - t0) / 1e3, (host[4096 + 192 + m] - t0) / 1e3);
-      if (sidx == 0) for (int m = 0; m < 8; ++m) fprintf(stderr, "[fkv p2 tile %2d] start %7.2f  tmem_ld %7.2f  votes %7.2f  bar %7.2f  pooled %7.2f\n", m,
-          (host[4096 + 256 + m] - t0) / 1e3, (host[4096 + 320 + m] - t0) / 1e3, (host[4096 + 384 + m] - t0) / 1e3, (host[4096 + 448 + m] - t0) / 1e3, (host[4096 + 512 + m] - t0) / 1e3);
-      fprintf(stderr, "[fkv trace] L=%d grid=%d %-10s min %8.2f us  avg %8.2f us  max %8.2f us\n", p.L, pl.grid, names[sidx], mn / 1e3, avg / pl.grid / 1e3, mx / 1e3);
+      fprintf(stderr, "[fkv trace] %-12s min %8.2f us  avg %8.2f us  max %8.2f us\n", names[sidx], mn / 1e3, avg / pl.grid / 1e3, mx / 1e3);
     }
   }
   return rc_launch;

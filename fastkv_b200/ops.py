@@ -81,14 +81,14 @@ def topk(src: torch.Tensor, k: int, *, order: int = L.ORDER_VALUE_DESC, tail: in
         stride_row, stride_sum = src.stride(0), src.stride(1)
     out = torch.empty((rows, k + tail), dtype=torch.int64, device=src.device)
     imp = torch.empty((rows, n), dtype=torch.float32, device=src.device) if (return_importance and nsum > 1) else None
-    ws = L.workspace(src.device, lib.fkv_topk_workspace_bytes(rows, n, k))
+    ws_ptr, ws_bytes = L.scratch(src.device, lib.fkv_topk_workspace_bytes(rows, n, k))
     p = L.TopkParams()
     p.struct_size = C.sizeof(L.TopkParams)
     p.rows, p.n, p.k, p.order, p.tail, p.nsum = rows, n, k, order, tail, nsum
     p.src, p.src_stride_row, p.src_stride_sum = src.data_ptr(), stride_row, stride_sum
     p.out, p.out_stride_row = out.data_ptr(), out.stride(0)
     p.imp_out = imp.data_ptr() if imp is not None else None
-    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    p.workspace, p.workspace_bytes = ws_ptr, ws_bytes
     L.check(lib.fkv_topk(C.byref(p), L.stream_ptr(src.device)))
     return (out, imp) if return_importance else out
 
@@ -162,7 +162,7 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, s
         raise ValueError("fastkv_b200: q needs a contiguous last dim")
     if out is None:
         out = torch.empty((B, Hq, D), dtype=q.dtype, device=q.device)
-    ws = L.workspace(q.device, lib.fkv_decode_workspace_bytes(B, Hq, D, Smax))
+    ws_ptr, ws_bytes = L.scratch(q.device, lib.fkv_decode_workspace_bytes(B, Hq, D, Smax))
     p = L.DecodeAttnParams()
     p.struct_size = C.sizeof(L.DecodeAttnParams)
     p.dtype, p.B, p.Hq, p.Hkv, p.D = L.dtype_code(q.dtype), B, Hq, Hkv, D
@@ -171,7 +171,7 @@ def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, s
     p.k_cache, p.v_cache = L.view4(k_cache), L.view4(v_cache)
     p.out, p.out_stride_b, p.out_stride_h = out.data_ptr(), out.stride(0), out.stride(1)
     p.seq_len_dev = seq_len_dev.data_ptr() if seq_len_dev is not None else None
-    p.workspace, p.workspace_bytes = ws.data_ptr(), ws.numel()
+    p.workspace, p.workspace_bytes = ws_ptr, ws_bytes
     L.check(lib.fkv_decode_attn(C.byref(p), L.stream_ptr(q.device)))
     return out
 

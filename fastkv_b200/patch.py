@@ -306,6 +306,10 @@ class GraphedDecode:
         with torch.cuda.graph(self.graph):
             self._step()
         # the capture itself did not execute: nothing to undo
+        # the graph bakes in the scratch pointer of the decode kernels: keep that buffer alive even if a
+        # later, larger call replaces it in the per-stream table
+        from . import _lib as _L
+        self._scratch_refs = list(_L._workspaces.values())
 
     @torch.no_grad()
     def _step(self):

@@ -211,7 +211,9 @@ int fkv_compress(const fkv_compress_params* p, void* stream);
 /* Bytes of scratch fkv_score / fkv_topk / fkv_compress need for these sizes (upper bound).     */
 /* A workspace must be passed through fkv_workspace_init ONCE after allocation: it zeroes the buffer,
  * i.e. the 256-byte header (departure counter + launch epoch of the scoring kernel) and the region
- * where CTAs exchange epoch-tagged partial softmax statistics.  Calls keep the header consistent. */
+ * where CTAs exchange epoch-tagged partial softmax statistics.  Calls keep the header consistent.
+ * The header is persistent state of fkv_score / fkv_compress: do not pass the same pointer as the
+ * scratch of fkv_topk / fkv_decode_attn (offset it by 256 bytes, or use a separate buffer). */
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int32_t L, int32_t window_size,
                            int32_t capacity, int32_t tsp_k);
