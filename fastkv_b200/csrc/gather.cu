@@ -22,6 +22,7 @@ struct GatherKvArgs {
 // warp moves 32 x 16 B = two 256-byte bf16 rows per instruction, fully coalesced on both sides.
 __global__ void __launch_bounds__(256)
 gather_kv_kernel(GatherKvArgs a) {
+  pdl_enter();
   const int hs = blockIdx.y, b = blockIdx.z;
   const int C = a.n_sel + a.W;
   const int lane_chunk = threadIdx.x % a.row_chunks;
@@ -72,6 +73,7 @@ struct GatherRowsArgs {
 // grid (T, B): one CTA per destination row; 8 KB bf16 hidden rows -> 512 x 16 B, two per thread.
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(GatherRowsArgs a) {
+  pdl_enter();
   const int i = blockIdx.x, b = blockIdx.y;
   const int64_t src_row = a.idx[(int64_t)b * a.idx_sb + i];
   const char* s = a.src + b * a.src_sb + src_row * a.src_sl;
@@ -104,8 +106,8 @@ int launch_gather_kv(const fkv_gather_kv_params& p, cudaStream_t s) {
   const int64_t heads = (int64_t)a.Hsel * p.B;
   while (rows_per_cta > rows_par && heads * ceil_div(C, rows_per_cta) < 2 * num_sms()) rows_per_cta -= rows_par;
   a.rows_per_cta = rows_per_cta;
-  gather_kv_kernel<<<dim3(ceil_div(C, rows_per_cta), a.Hsel, p.B), 256, 0, s>>>(a);
-  FKV_LAUNCH_CHECK();
+  FKV_CUDA_TRY(launch_pdl(gather_kv_kernel, dim3(ceil_div(C, rows_per_cta), a.Hsel, p.B), dim3(256), 0, s, a));
+  count_launch();
   return FKV_OK;
 }
 
@@ -118,8 +120,8 @@ int launch_gather_rows(const fkv_gather_rows_params& p, cudaStream_t s) {
   a.idx = p.idx; a.idx_sb = p.idx_stride_b;
   a.pos_in = p.pos_in; a.pos_sb = p.pos_stride_b; a.pos_out = p.pos_out; a.pos_out_sb = p.pos_out_stride_b;
   a.T = p.T;
-  gather_rows_kernel<<<dim3(p.T, p.B), 256, 0, s>>>(a);
-  FKV_LAUNCH_CHECK();
+  FKV_CUDA_TRY(launch_pdl(gather_rows_kernel, dim3(p.T, p.B), dim3(256), 0, s, a));
+  count_launch();
   return FKV_OK;
 }
 

@@ -164,8 +164,20 @@ __device__ __forceinline__ void ld_record(const unsigned long long* p, unsigned 
 
 // balanced split of U units over the grid: u0(c) = floor(c * U / grid); with fewer units than CTAs the
 // first U CTAs take one unit each, so the CTAs that share a (b, h) pair are always consecutive and non-empty
-__device__ __forceinline__ int unit_begin(int c, int U, int grid) { return U >= grid ? (int)((long long)c * U / grid) : min(c, U); }
-__device__ __forceinline__ int cta_of_unit(long long u, int U, int grid) { return U >= grid ? (int)(((u + 1) * grid - 1) / U) : (int)u; }
+// (32-bit arithmetic: the plan guarantees U * grid < 2^31)
+__device__ __forceinline__ int unit_begin(int c, int U, int grid) {
+  return U >= grid ? (int)((unsigned)c * (unsigned)U / (unsigned)grid) : min(c, U);
+}
+__device__ __forceinline__ int cta_of_unit(int u, int U, int grid) {
+  return U >= grid ? (int)((((unsigned)u + 1u) * (unsigned)grid - 1u) / (unsigned)U) : u;
+}
+
+// warp-wide float max in one instruction (CREDUX, sm_100a)
+__device__ __forceinline__ float warp_max_f32(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
 
 template <int W, int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -233,7 +245,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  asm volatile("griddepcontrol.wait;" ::: "memory");   // no-op unless launched as a programmatic dependent
+  pdl_enter();                                      // nothing global is touched before this point
   if (threadIdx.x == 64) FKV_TRACE(1);
 
   if (warp == 0) {
@@ -415,7 +427,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             Z += v.y * ex2(v.x - M);
           }
           const int pr = pair0 + flushed;
-          const int krank = cta - cta_of_unit((long long)(pr - p0) * a.n_tiles, Uph, grid);
+          const int krank = cta - cta_of_unit((pr - p0) * a.n_tiles, Uph, grid);
           st_record(a.part + (((size_t)pr * a.maxc + krank) * N + et) * 2, tag_word(M, tag_m), tag_word(Z, tag_z));
         }
         named_bar(2, kEpiThreads);
@@ -448,22 +460,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
 #pragma unroll
       for (int n = 0; n < N; ++n) dmax = fmaxf(dmax, fmaf(s[n], a.c, -mn[n]));
       if (__any_sync(0xffffffffu, own && dmax > kLazyTau)) {
-        // rare (always on the first tile of a pair): raise the references, 8 rows per round
+        // rare (always on the first tile of a pair): raise the references to the warp-wide column max
 #pragma unroll
-        for (int n0 = 0; n0 < N; n0 += 8) {
-          float cm[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cm[i] = own ? s[n0 + i] * a.c : -INFINITY;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) cm[i] = fmaxf(cm[i], __shfl_xor_sync(0xffffffffu, cm[i], o));
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float nm = fmaxf(mn[n0 + i], cm[i]);
-            z[n0 + i] *= ex2(mn[n0 + i] - nm);
-            mn[n0 + i] = nm;
-          }
+        for (int n = 0; n < N; ++n) {
+          const float nm = fmaxf(mn[n], warp_max_f32(own ? s[n] * a.c : -INFINITY));
+          z[n] *= ex2(mn[n] - nm);
+          mn[n] = nm;
         }
       }
       if (own) {
@@ -481,7 +483,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // No grid barrier: a CTA only needs the partials of the CTAs that share its (b, h) pairs, and every
     // record says by itself whether it belongs to this launch.
     if (et < nlp) {
-      const long long ub = (long long)(pair0 + et - p0) * a.n_tiles;
+      const int ub = (pair0 + et - p0) * a.n_tiles;
       ncontrib[et] = cta_of_unit(ub + a.n_tiles - 1, Uph, grid) - cta_of_unit(ub, Uph, grid) + 1;
     }
     named_bar(2, kEpiThreads);
@@ -694,7 +696,7 @@ Plan make_plan(const fkv_score_params& p) {
   if (pl.S < 32) return pl;
   pl.n_tiles = ceil_div(p.L, pl.S);
   const long long U = (long long)p.B * pl.nkv * pl.n_tiles;
-  if (U > (1ll << 30)) return pl;
+  if (U * num_sms() >= (1ll << 31)) return pl;        // the kernel splits units with 32-bit arithmetic
   pl.U = (int)U;
   pl.grid = (int)(U < num_sms() ? U : num_sms());
   // phases: groups of `ppp` (b, h) pairs whose tiles fit in the TMEM blocks of the CTAs (<= NB tiles per
@@ -752,7 +754,7 @@ int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, i
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (mode_env && mode_env[0] == 'c') ? 1 : 2;     // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
+  cfg.numAttrs = ((mode_env && mode_env[0] == 'c') || !pdl_enabled()) ? 1 : 2;     // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
   FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G>, mk, mq, a));
   count_launch();
   return FKV_OK;

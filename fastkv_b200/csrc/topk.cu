@@ -312,6 +312,7 @@ topk_cluster_kernel(TopkArgs a) {
   for (int i = tid; i < kMaxBins; i += kThreads) { sm.hist[i] = 0; sm.ghist[i] = 0; }
   if (tid < 16) sm.bc[tid] = 0;
   csync();                                          // the leader's ghist is zero before anybody adds to it
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // programmatic dependent launch: the producer of `src` has completed
 
   // ---- 1. load the slice (fixed-order head sum for TSP), keys -> smem ---------------------------------
   const int per_cta = ((n + C - 1) / C + 3) & ~3;
@@ -747,11 +748,13 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = sizeof(ClusterSmem);
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = Cp; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     static const bool trace_on = getenv("FKV_TOPK_TRACE") != nullptr;
     static unsigned long long* trace_buf = nullptr;
     if (trace_on) {
