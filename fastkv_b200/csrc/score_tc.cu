@@ -42,7 +42,8 @@ struct TcArgs {
   int U, maxlp, nst, maxc;
   int npairs, ppp, nph;                                 // (b, h) pairs, pairs per phase, phases
   int kpos_l, kpos_h, kpos_b, qpos_l, qpos_h, qpos_b;   // coordinate slots of the stride-sorted TMA dims
-  int q_heads_per_kv;                                   // model G (query head = kvh * G + g)
+  int q_heads_per_kv;                                   // model G (query head = kvh * G + g0 + g)
+  int g0, accumulate;                                   // head sub-group of this launch; add to the score already there
   float c;                                              // softmax scale * log2(e)
   unsigned long long* part;                             // [pair][contributor rank][N][2] epoch-tagged (max | sum) words
   unsigned int* sync_counter;                           // workspace header: [1] departures (left zero), u64 at [2] = launch epoch
@@ -185,7 +186,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   constexpr int N = W * G;                          // logit rows per (b, kv head)
   constexpr int NMMA = N < 16 ? 16 : N;             // UMMA N (multiple of 16 for M = 128)
   constexpr int NB = 512 / NMMA;                    // accumulator blocks: ALL of TMEM is a logits cache
-  static_assert(N <= 64 && (N & 7) == 0, "unsupported window x group size");
+  static_assert(N <= 32 && (N & 7) == 0, "unsupported window x group size");
 
   extern __shared__ unsigned char smem_dyn[];
   if (threadIdx.x == 64) FKV_TRACE(0);
@@ -292,7 +293,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             for (int slab = 0; slab < slabs; ++slab)
 #pragma unroll
               for (int g = 0; g < G; ++g) {
-                const int hq = pkvh * a.q_heads_per_kv + g;
+                const int hq = pkvh * a.q_heads_per_kv + a.g0 + g;
                 tma_load_4d(qdst + slab * (NMMA * 128) + g * (W * 128), &tm_q, bar_qfull(qb), slab * 64,
                             a.P * ql1 + hq * qh1 + pb * qb1, a.P * ql2 + hq * qh2 + pb * qb2, a.P * ql3 + hq * qh3 + pb * qb3);
               }
@@ -559,7 +560,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       named_bar(3 + wg, 128);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
       if (own) {
-        float acc = 0.f;
+        // a later head sub-group continues the sum of the earlier launches: ((p0 + p1) + p2) + p3 as in utils.py:112
+        float acc = a.accumulate ? a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] : 0.f;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           float pooled;
@@ -581,7 +583,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             pooled = sum * inv_ks;                    // count_include_pad: always / kernel_size
           }
           if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
-          else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * G + g - a.out_h0) * a.score_sh + key] = pooled;
+          else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * a.q_heads_per_kv + a.g0 + g - a.out_h0) * a.score_sh + key] = pooled;
         }
         if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
       }
@@ -672,7 +674,7 @@ int make_map(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int 
 }
 
 struct Plan {
-  int G, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst, maxc, npairs, ppp, nph;
+  int G, Gm, W, N, nkv, kv0, n_tiles, S, half, U, grid, maxlp, nst, maxc, npairs, ppp, nph;   // G = heads per launch, Gm = model group size
   size_t smem, part_bytes;
   bool ok;
 };
@@ -683,8 +685,14 @@ Plan make_plan(const fkv_score_params& p) {
   if (p.dtype != FKV_BF16 && p.dtype != FKV_F16) return pl;
   if (p.mode != FKV_MODE_FASTKV && p.mode != FKV_MODE_SNAPKV) return pl;
   const int Gm = p.Hq / p.Hkv;
-  pl.G = Gm; pl.W = p.window_size; pl.N = pl.G * pl.W;
-  if (!(pl.W == 8 || pl.W == 16 || pl.W == 32) || pl.N > 64) return pl;
+  pl.W = p.window_size;
+  if (!(pl.W == 8 || pl.W == 16 || pl.W == 32)) return pl;
+  // At most 32 logit rows per MMA tile (running max + sum + logits = 96 live registers per epilogue thread):
+  // wider groups (W=16/32 at G=4, G=8 models) run as several launches over head sub-groups, each reading K once.
+  int Gk = Gm;
+  while (Gk > 1 && (Gk * pl.W > 32 || Gm % Gk)) --Gk;
+  if (Gk * pl.W > 32) return pl;
+  pl.G = Gk; pl.Gm = Gm; pl.N = pl.G * pl.W;
   if (p.mode == FKV_MODE_SNAPKV) {
     if (p.h0 % Gm || p.h1 % Gm) return pl;           // whole kv-head groups only
     pl.kv0 = p.h0 / Gm; pl.nkv = (p.h1 - p.h0) / Gm;
@@ -772,7 +780,7 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   a.B = p.B; a.L = p.L; a.P = p.L - p.window_size; a.D = p.D;
   a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
   a.pooling = p.pooling; a.group_sum = (p.mode == FKV_MODE_FASTKV); a.is_f16 = (p.dtype == FKV_F16);
-  a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.maxc = pl.maxc; a.q_heads_per_kv = pl.G;
+  a.U = pl.U; a.maxlp = pl.maxlp; a.nst = pl.nst; a.maxc = pl.maxc; a.q_heads_per_kv = pl.Gm;
   a.npairs = pl.npairs; a.ppp = pl.ppp; a.nph = pl.nph;
   a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
   char* ws = reinterpret_cast<char*>(p.workspace);
@@ -791,13 +799,16 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
     a.trace = trace_buf;
   }
 
-#define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) return launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
   int rc_launch = FKV_EMODE;
-#undef FKV_TC_CASE
 #define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) rc_launch = launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
-  FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4); FKV_TC_CASE(8, 8);
-  FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2); FKV_TC_CASE(16, 4);
-  FKV_TC_CASE(32, 1); FKV_TC_CASE(32, 2);
+  for (int g0 = 0; g0 < pl.Gm; g0 += pl.G) {         // one launch per head sub-group (a single one for W*G <= 32)
+    a.g0 = g0;
+    a.accumulate = (a.group_sum && g0 > 0) ? 1 : 0;
+    FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4);
+    FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2);
+    FKV_TC_CASE(32, 1);
+    if (rc_launch != FKV_OK) return rc_launch;
+  }
 #undef FKV_TC_CASE
   if (trace_on && rc_launch == FKV_OK) {                // debugging aid only: synchronises and prints phase times
     cudaStreamSynchronize(s);

@@ -223,6 +223,36 @@ def test_simple_and_auto_paths_select_identically_on_clear_gaps():
     check_selection(sa, ca.last_aux["idx"].reshape(sa.shape[0], -1), cb.last_aux["idx"].reshape(sa.shape[0], -1))
 
 
+_PHASE_CHECK = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from fastkv_b200 import ops, _lib as L
+from parity_utils import make_inputs
+for (b, hq, hkv, l, w, ks, pool) in [(2, 16, 4, 1500, 8, 7, "avgpool"), (3, 8, 8, 700, 8, 5, "maxpool"), (1, 32, 8, 4099, 8, 7, "avgpool"),
+                                     (2, 16, 4, 2048, 16, 13, "avgpool"), (1, 16, 4, 1000, 32, 7, "avgpool")]:
+    q, k, v = [x.cuda() for x in make_inputs(l + b, b, hq, hkv, l, 128)]
+    ref = ops.score(q, k, window_size=w, kernel_size=ks, pooling=pool, impl=L.IMPL_SIMPLE).double()
+    got = ops.score(q, k, window_size=w, kernel_size=ks, pooling=pool, impl=L.IMPL_TENSOR).double()
+    torch.cuda.synchronize()
+    scale = ref.abs().amax(-1, keepdim=True)
+    err = ((ref - got).abs() / (ref.abs() + 1e-3 * scale)).max().item()
+    assert err < 2e-5 and not torch.isnan(got).any(), (b, hq, hkv, l, w, ks, pool, err)
+print("phases ok")
+"""
+
+
+@pytest.mark.parametrize("ppp", ["1", "2", "3"])
+def test_scoring_kernel_phase_loop_at_small_sizes(ppp):
+    """FKV_TC_PPP caps the (b, h) pairs per phase, so the multi-phase path of the tcgen05 kernel (TMEM
+    blocks recycled between phases, per-phase partial exchange) runs at sizes the fp32 path checks in
+    milliseconds.  The knob is read once per process, hence the subprocess."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FKV_TC_PPP=ppp)
+    r = subprocess.run([sys.executable, "-c", _PHASE_CHECK, root], env=env, capture_output=True, text=True, timeout=170)
+    assert r.returncode == 0 and "phases ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ---------------------------------------------------------------------------------------------
 # full BASELINE sizes: size-independent properties (the oracle would take minutes here)
 # ---------------------------------------------------------------------------------------------

@@ -105,9 +105,9 @@ def main():
     for c in cfgs:
         tot, sc = run_one(**c)
         nb = alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"])
-        impl = "tcgen05" if (c["mode"] != "gemfilter" and c["w"] * (HQ // HKV if c["mode"] == "fastkv" else 1) <= 64) else "simt"
-        if c["mode"] == "fastkv" and c["w"] * 4 > 64:
-            impl = "simt"
+        impl = "simt" if c["mode"] == "gemfilter" else "tcgen05"
+        if impl == "tcgen05" and c["w"] * (HQ // HKV) > 32:
+            impl += " x%d head groups" % (c["w"] * (HQ // HKV) // 32)
         gbs = nb / tot / 1e3
         rows.append(f"| {c['mode']} | {c['b']} | {c['l']} | {c['c']} | {c['w']} | {c['ks']} | {c['pool']} | {impl} | {tot:.1f} | {sc:.1f} | "
                     f"{nb / 1e6:.1f} | {gbs:.0f} | {gbs / a.peak:.2f} |")

@@ -16,7 +16,8 @@ def timeit(fn, reps=20):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 for (b, hq, hkv, l, w, ks, pool) in [(1, 32, 8, 2048, 8, 7, 'avgpool'), (1, 32, 8, 4099, 8, 7, 'avgpool'), (2, 16, 4, 2048, 16, 5, 'maxpool'),
-                                     (1, 32, 8, 32768, 8, 7, 'avgpool'), (1, 8, 8, 1500, 8, 7, 'avgpool'), (1, 32, 8, 3000, 16, 13, 'avgpool'),
+                                     (1, 32, 8, 32768, 8, 7, 'avgpool'), (1, 8, 8, 1500, 8, 7, 'avgpool'), (1, 32, 8, 3000, 16, 13, 'avgpool'), (2, 32, 8, 5000, 32, 7, 'avgpool'), (1, 64, 8, 4000, 8, 7, 'maxpool'),
+                                     (1, 32, 8, 32768, 16, 7, 'avgpool'), (1, 32, 8, 32768, 32, 7, 'avgpool'),
                                      (8, 32, 8, 32768, 8, 7, 'avgpool'), (1, 32, 8, 131072, 8, 7, 'avgpool')]:
     q, k, v = [x.cuda() for x in make_inputs(l, b, hq, hkv, l, 128)]
     s_simple = ops.score(q, k, window_size=w, kernel_size=ks, pooling=pool, impl=L.IMPL_SIMPLE)
