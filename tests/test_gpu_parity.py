@@ -159,6 +159,22 @@ def test_gemfilter_matches_reference_golden(name):
         assert torch.equal(torch.sort(got[0, 0].cpu()).values, fx["sorted_indices"])
 
 
+@pytest.mark.parametrize("b,hq,hkv,l,d,ks", [(1, 32, 8, 5000, 128, 5), (2, 16, 4, 1234, 128, 5), (1, 8, 8, 700, 64, 5),
+                                             (1, 32, 8, 32768, 128, 5), (3, 16, 2, 300, 128, 7)])
+def test_gemfilter_tensor_path_matches_fp32_path(b, hq, hkv, l, d, ks):
+    """tcgen05 GemFilter scores (sum over kv heads inside the TMEM accumulator) vs the fp32 CUDA-core path."""
+    from fastkv_b200 import ops
+    L = _lib()
+    q, k, _ = [x.to(DEV) for x in make_inputs(l + hq, b, hq, hkv, l, d)]
+    ref = ops.score(q, k, window_size=1, kernel_size=ks, mode=L.MODE_GEMFILTER, impl=L.IMPL_SIMPLE).double()
+    got = ops.score(q, k, window_size=1, kernel_size=ks, mode=L.MODE_GEMFILTER, impl=L.IMPL_TENSOR).double()
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (b, 1, l)
+    # head-summed dot products cancel: compare against the magnitude of the terms, not of the (small) sum
+    scale = ref.abs().amax(-1, keepdim=True)
+    assert ((ref - got).abs() / scale).max().item() < 2e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # seeded inputs against the oracle at sizes it finishes in seconds
 # ---------------------------------------------------------------------------------------------

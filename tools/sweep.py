@@ -105,7 +105,7 @@ def main():
     for c in cfgs:
         tot, sc = run_one(**c)
         nb = alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"])
-        impl = "simt" if c["mode"] == "gemfilter" else "tcgen05"
+        impl = "tcgen05"
         if impl == "tcgen05" and c["w"] * (HQ // HKV) > 32:
             impl += " x%d head groups" % (c["w"] * (HQ // HKV) // 32)
         gbs = nb / tot / 1e3
