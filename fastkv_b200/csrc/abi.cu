@@ -224,6 +224,9 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   char* ws = reinterpret_cast<char*>(sp.workspace);
   cudaStream_t s = (cudaStream_t)stream;
 
+  // short contexts (post-TSP layers): score + top-k + compaction in one cluster kernel
+  if (small_compress_supported(*p)) return launch_small_compress(*p, s);
+
   if ((rc = run_score(sp, s)) != FKV_OK) return rc;
 
   // per-head top-k needs rows addressed as one flat list: require the dense [B,Hsel,P] layout

@@ -217,6 +217,52 @@ def test_fastkv_seeded_vs_oracle(case, dtype):
             assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
 
 
+SHORT_CASES = [
+    # b, hq, hkv, L, D, ks, pooling, C, dist   (window 8, no TSP at this layer, L <= 3904: the one-kernel cluster path)
+    (1, 32, 8, 2048, 128, 7, "avgpool", 2048, "gauss"),       # the post-TSP layer of BASELINE configs[1]: L == C, full re-order
+    (1, 32, 8, 2048, 128, 7, "avgpool", 512, "peaky"),
+    (2, 16, 4, 3900, 128, 7, "avgpool", 256, "gauss"),        # 32 tiles: 4 per CTA, batch 2
+    (1, 8, 8, 300, 64, 5, "avgpool", 64, "gauss"),            # MHA (G=1), D=64, fewer tiles than CTAs in the cluster
+    (3, 8, 4, 1000, 128, 13, "maxpool", 128, "gauss"),        # G=2, maxpool, kernel 13
+    (1, 32, 8, 130, 128, 7, "avgpool", 40, "gauss"),          # two tiles only
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("case", SHORT_CASES)
+def test_short_context_fused_kernel_vs_oracle(case, dtype, monkeypatch):
+    """Opt-in path (FKV_SMALL_FUSE=1): non-TSP layers with a short context run score + top-k + compaction as
+    ONE cluster kernel (small_compress_kernel); same checks as the three-kernel path."""
+    monkeypatch.setenv("FKV_SMALL_FUSE", "1")
+    before = _lib().load().fkv_launch_count()
+    b, hq, hkv, l, d, ks, pooling, c, dist = case
+    g, w = hq // hkv, 8
+    q, k, v = make_inputs(500 + l + c, b, hq, hkv, l, d, dtype=torch.float32, dist=dist)
+    if dtype == torch.float16:
+        q, k, v = [x.clamp(-8, 8) for x in (q, k, v)]
+    knobs = dict(window_size=w, max_capacity_prompt=c, kernel_size=ks, pooling=pooling, tsp_layer=False, tsp_length=2048)
+    ref = O.fastkv_update_kv(k, q, v, g, **knobs)
+    cl, (ko, vo, tsp) = _run_cluster(knobs, k.to(DEV, dtype), q.to(DEV, dtype), v.to(DEV, dtype), g, _lib().IMPL_AUTO)
+    aux = cl.last_aux
+    assert _lib().load().fkv_launch_count() - before == 1, "the fused kernel did not run"
+    assert tsp is None and ko.shape == (b, hkv, c, d)
+    check_scores_close(ref.score, aux["score"], SCORE_RTOL, "fused")
+    check_topk_consistent(aux["score"], aux["idx"])
+    check_compaction_exact(k.to(dtype), v.to(dtype), aux["idx"], ko, vo, w)
+    if pooling == "avgpool":
+        flat = ref.score.reshape(-1, ref.score.shape[-1])
+        check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), "fused")
+    else:
+        ours = torch.gather(ref.score, -1, aux["idx"].cpu()).sort(-1).values
+        theirs = torch.gather(ref.score, -1, ref.idx).sort(-1).values
+        assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+    # and the three-kernel path on the same inputs selects the same rows wherever the gaps are clear
+    cs, (ks_, vs_, _) = _run_cluster(knobs, k.to(DEV, dtype), q.to(DEV, dtype), v.to(DEV, dtype), g, _lib().IMPL_SIMPLE)
+    sa = cs.last_aux["score"].reshape(-1, cs.last_aux["score"].shape[-1])
+    if pooling == "avgpool":
+        check_selection(sa, cs.last_aux["idx"].reshape(sa.shape[0], -1), aux["idx"].reshape(sa.shape[0], -1), "fused vs simple")
+
+
 def test_strided_blhd_views_equal_contiguous_inputs():
     """update_kv gets [B,H,L,D] views of [B,L,H,D] memory; results must not depend on the layout."""
     knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)
