@@ -1388,13 +1388,12 @@ int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, i
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
-  static const char* mode_env = getenv("FKV_TC_LAUNCH");        // FKV_TC_LAUNCH=coop turns the programmatic-launch attribute off
   attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: CTAs wait on each other's partials
   attr[0].val.cooperative = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = ((mode_env && mode_env[0] == 'c') || !pdl_enabled()) ? 1 : 2;     // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;             // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
   FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G>, mk, mq, a));
   count_launch();
   return FKV_OK;

@@ -715,8 +715,6 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
   // CTAs per row: ~4096 keys per CTA (short phases), at least enough for the slice to fit in smem
   long long want = ((long long)p.n * a.nsum + kTargetKeys - 1) / kTargetKeys;   // summed rows read nsum x the bytes
   int C = (int)(want > kMaxCluster ? kMaxCluster : (want < 1 ? 1 : want));
-  static const int small_fuse = getenv("FKV_TOPK_SMALL_FUSE") ? atoi(getenv("FKV_TOPK_SMALL_FUSE")) : 0;
-  if (fg && small_fuse > 1 && C < small_fuse) C = small_fuse;   // experiment: spread small rows to fuse the copy
   const bool fits = ceil_div(p.n, kMaxCluster) <= kSliceKeys;
   if (!no_cluster && fits && p.k <= kKmax && (p.src_stride_row % 4) == 0) {
     int Cp = 1;

@@ -263,6 +263,26 @@ def test_short_context_fused_kernel_vs_oracle(case, dtype, monkeypatch):
         check_selection(sa, cs.last_aux["idx"].reshape(sa.shape[0], -1), aux["idx"].reshape(sa.shape[0], -1), "fused vs simple")
 
 
+def test_scratch_users_leave_the_scoring_header_alone():
+    """The scoring kernel keeps its departure counter + launch epoch in the first 256 bytes of the shared
+    per-stream workspace; top-k (generic path, global sort scratch) and decode attention use the same buffer
+    as plain scratch and must not clobber it (a clobbered epoch makes stale partial records look valid)."""
+    from fastkv_b200 import ops
+    L = _lib()
+    q, k, v = [x.to(DEV, torch.bfloat16) for x in make_inputs(77, 1, 32, 8, 9000, 128)]
+    run = lambda: ops.compress(q, k, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=512, tsp_len=1024, return_aux=True)
+    k0, v0, t0, aux0 = run()
+    big = torch.rand(2, 60000, device=DEV)
+    ops.topk(big, 30000)                                            # k > 2048: generic path, sorts in the workspace
+    qd = torch.randn(2, 32, 128, device=DEV, dtype=torch.bfloat16)
+    kc = torch.randn(2, 8, 4096, 128, device=DEV, dtype=torch.bfloat16)
+    ops.decode_attn(qd, kc, kc.clone(), 4000)                       # split-K partials in the workspace
+    for _ in range(3):
+        k1, v1, t1, aux1 = run()
+        assert torch.equal(k0, k1) and torch.equal(v0, v1) and torch.equal(t0, t1)
+        assert torch.equal(aux0["score"], aux1["score"])
+
+
 def test_strided_blhd_views_equal_contiguous_inputs():
     """update_kv gets [B,H,L,D] views of [B,L,H,D] memory; results must not depend on the layout."""
     knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)
