@@ -602,6 +602,7 @@ topk_cluster_kernel(TopkArgs a) {
   }
   TK_TRACE(5);
   csync();
+  TK_TRACE(7);
   if (by_value) {
     if (a.g.enabled) {
       // ---- 4b. fused KV compaction (baselines/fastkv/utils.py:114-121): the whole cluster copies the
@@ -640,6 +641,7 @@ topk_cluster_kernel(TopkArgs a) {
           }
       }
     }
+    TK_TRACE(6);
     return;
   }
 
@@ -766,7 +768,7 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
       unsigned long long h[16];
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[topk trace] n=%d rows=%d C=%d order=%d:", p.n, p.rows, Cp, p.order);
-      for (int i = 1; i <= 6; ++i) fprintf(stderr, " %d:%.2f", i, (double)(h[i] - h[0]) / 1e3);
+      for (int i = 1; i <= 7; ++i) fprintf(stderr, " %d:%.2f", i, (double)(h[i] - h[0]) / 1e3);
       fprintf(stderr, "\n");
     }
     return FKV_OK;

@@ -78,6 +78,9 @@ def set_model(model, args):
         raise ValueError("max_capacity_prompts == -1 is not supported")
     if args.method == "fullkv":
         return
+    if args.method == "gemfilter":                             # monkeypatch.py:149-151
+        set_topk(model, args, mode="gemfilter")
+        return
     if args.method not in ("fastkv", "snapkv"):
         raise NotImplementedError(f"method {args.method!r} is outside the FastKV hot path")
     window_size, kernel_size, pooling, retain_rate = args.window_size, args.kernel_size, args.pooling, args.retain_rate
@@ -242,6 +245,39 @@ def _make_forwards(mod, method, sliding_window_attr=False):
     return attn_forward, decoder_forward, model_forward
 
 
+def _make_gemfilter_attn_forward(mod, sliding_window_attr=False):
+    """Attention forward of the GemFilter baseline (baselines/gemfilter/llama_model.py:104-160, mistral twin):
+    in select mode the selection layer records the token indices (``find_context``, our ``fkv_score`` GemFilter
+    mode + ``fkv_topk``) and nothing is cached; otherwise stock attention with a stock cache update."""
+    apply_rotary_pos_emb = mod.apply_rotary_pos_emb
+    eager_attention_forward = mod.eager_attention_forward
+    ALL_ATTENTION_FUNCTIONS = mod.ALL_ATTENTION_FUNCTIONS
+    from .cluster import find_context
+
+    def attn_forward(self, hidden_states, position_embeddings=None, attention_mask=None, past_key_values=None, **kwargs):
+        input_shape = hidden_states.shape[:-1]
+        hidden_shape = (*input_shape, -1, self.head_dim)
+        query_states = self.q_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        key_states = self.k_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        value_states = self.v_proj(hidden_states).view(hidden_shape).transpose(1, 2)
+        cos, sin = position_embeddings
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
+        if self.select_mode:                                   # llama_model.py:141-143
+            self.indecies = None
+            find_context(self, query_states, key_states)
+        if not self.select_mode and past_key_values is not None:   # :145-150
+            key_states, value_states = past_key_values.update(key_states, value_states, self.layer_idx)
+        attention_interface = ALL_ATTENTION_FUNCTIONS.get_interface(self.config._attn_implementation, eager_attention_forward)
+        extra = {"sliding_window": getattr(self.config, "sliding_window", None)} if sliding_window_attr else {}
+        attn_output, attn_weights = attention_interface(
+            self, query_states, key_states, value_states, attention_mask,
+            dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **extra, **kwargs)
+        attn_output = self.o_proj(attn_output.reshape(*input_shape, -1).contiguous())
+        return attn_output, attn_weights
+
+    return attn_forward
+
+
 def _patch(mod, prefix, method, sliding):
     attn_cls = getattr(mod, prefix + "Attention")
     layer_cls = getattr(mod, prefix + "DecoderLayer")
@@ -253,8 +289,25 @@ def _patch(mod, prefix, method, sliding):
     if method == "fullkv":
         attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__ = o_attn, o_layer, o_model, o_init
         return
+    if method == "gemfilter":
+        # selection-mode baseline: only the attention forward differs from stock (gemfilter/llama_model.py)
+        gf_forward = _make_gemfilter_attn_forward(mod, sliding_window_attr=sliding)
+
+        def gemfilter_init(self, *args, **kwargs):             # LlamaGemFilterAttention.__init__ (:88-98)
+            o_init(self, *args, **kwargs)
+            self.indecies = None
+            self.topk = 1024
+            self.rate = 0.25
+            self.retain_rate = 0.25
+            self.eviction_mode = "constant"
+            self.select_layer_idx = 13
+            self.select_mode = False
+
+        attn_cls.__init__, attn_cls.forward = gemfilter_init, gf_forward
+        layer_cls.forward, model_cls.forward = o_layer, o_model
+        return
     if method not in ("fastkv", "snapkv"):
-        raise NotImplementedError(f"No method found for {method}: only fastkv / snapkv / fullkv are on the hot path")
+        raise NotImplementedError(f"No method found for {method}: only fastkv / snapkv / gemfilter / fullkv are on the hot path")
     attn_f, layer_f, model_f = _make_forwards(mod, method, sliding_window_attr=sliding)
 
     def patched_init(self, *args, **kwargs):
@@ -346,3 +399,98 @@ def greedy_generate(model, input_ids, genlen, attention_mask=None, max_new_token
         tok = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
         toks.append(tok)
     return torch.cat(toks, dim=1), cache
+
+
+# ---------------------------------------------------------------------------------------------
+# GemFilter two-pass driver (baselines/gemfilter/utils.py:58-158)
+# ---------------------------------------------------------------------------------------------
+def set_topk(model, args, mode="gemfilter"):
+    """gemfilter/utils.py:78-89."""
+    if mode != "gemfilter":
+        raise NotImplementedError
+    for layer in model.model.layers:
+        layer.self_attn.topk = args.max_capacity_prompts
+        layer.self_attn.retain_rate = args.retain_rate
+        layer.self_attn.eviction_mode = args.eviction_mode
+
+
+def set_select_mode(model, mode):
+    """gemfilter/utils.py:91-95."""
+    for layer in model.model.layers:
+        layer.self_attn.select_mode = mode
+
+
+def set_select_layer(model, select_layer_idx):
+    """gemfilter/utils.py:97-104."""
+    if select_layer_idx is None:
+        return model.model.layers[0].self_attn.select_layer_idx
+    for layer in model.model.layers:
+        layer.self_attn.select_layer_idx = select_layer_idx
+    return select_layer_idx
+
+
+def reduce_layer(model, layer_idx):
+    """gemfilter/utils.py:68-71: run only layers [0, layer_idx] in the selection pass."""
+    original_layers = model.model.layers
+    model.model.layers = model.model.layers[:layer_idx + 1]
+    return model, original_layers
+
+
+def recover_layer(model, layers):
+    """gemfilter/utils.py:73-75."""
+    model.model.layers = layers
+    return model
+
+
+def get_layer_context(model, tokenizer, input_ids, layer_idx, print_context=False):
+    """gemfilter/utils.py:58-66: the selected token ids in their original order, shape [1, k]."""
+    idx = model.model.layers[layer_idx].self_attn.indecies[0, 0, :]
+    values, _ = torch.sort(idx)
+    new_input_ids = input_ids.gather(0, values.to(input_ids.device))
+    if print_context and tokenizer is not None:
+        print(tokenizer.decode(new_input_ids))
+    return new_input_ids.unsqueeze(0)
+
+
+@torch.no_grad()
+def gemfilter_generate_selection_prefill(input_ids, attn_mask, model, tokenizer=None, select_layer_idx=None, print_context=False):
+    """gemfilter/utils.py:140-158: pass 1 over layers [0, select layer] picks the tokens, pass 2 prefills the
+    whole model on them.  Returns (first predicted token [1,1], past_key_values)."""
+    set_select_mode(model, True)
+    select_layer_idx = set_select_layer(model, select_layer_idx)
+    model, original_layers = reduce_layer(model, select_layer_idx)
+    try:
+        model(input_ids, attention_mask=attn_mask, use_cache=False, logits_to_keep=1)
+        new_input_ids = get_layer_context(model, tokenizer, input_ids[0], select_layer_idx, print_context=print_context)
+    finally:
+        model = recover_layer(model, original_layers)
+        set_select_mode(model, False)
+    outputs = model(new_input_ids, use_cache=True, logits_to_keep=1)
+    pred_token_idx = outputs.logits[:, -1, :].argmax(dim=-1).unsqueeze(1)
+    return pred_token_idx, outputs.past_key_values
+
+
+@torch.no_grad()
+def gemfilter_generate(model, tokenizer, pred_token_idx, past_key_values, max_gen_len):
+    """gemfilter/utils.py:107-121 (greedy loop; stops at the tokenizer's EOS when a tokenizer is given)."""
+    eos = getattr(tokenizer, "eos_token_id", None)
+    generated_ids = [pred_token_idx.item()]
+    for _ in range(max_gen_len):
+        outputs = model(input_ids=pred_token_idx, past_key_values=past_key_values, use_cache=True)
+        past_key_values = outputs.past_key_values
+        pred_token_idx = outputs.logits[:, -1, :].argmax(dim=-1).unsqueeze(1)
+        if eos is not None and pred_token_idx.item() == eos:
+            break
+        generated_ids.append(pred_token_idx.item())
+    return generated_ids
+
+
+@torch.no_grad()
+def gemfilter_generate_selection(input_ids, attn_mask, model, tokenizer=None, max_gen_len=50, select_layer_idx=None,
+                                 print_context=False):
+    """gemfilter/utils.py:123-138.  Returns the decoded string with a tokenizer, the token ids without one."""
+    pred, cache = gemfilter_generate_selection_prefill(input_ids, attn_mask, model, tokenizer, select_layer_idx, print_context)
+    output_ids = gemfilter_generate(model, tokenizer, pred, cache, max_gen_len=max_gen_len)
+    if tokenizer is None:
+        return output_ids
+    return tokenizer.decode(output_ids, skip_special_tokens=True).strip()

@@ -119,3 +119,42 @@ def test_graphed_decode_matches_eager_decode(patched):
     assert got.shape == (2, 9)
     assert torch.equal(got, eager)
     assert out.past_key_values.get_seq_length(0) == cache_e.get_seq_length(0) == 128 + 8
+
+
+def test_gemfilter_two_pass_driver_selects_like_the_oracle():
+    """GemFilter (SURVEY.md §8 a13 + §8f rank 4): pass 1 over layers [0, select layer] records the indices with the
+    tensor-core GemFilter kernel; they must be the oracle's top-k of the same layer's q/k, pass 2 prefills on exactly
+    those tokens in their original order, and decoding continues from that cache."""
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    from fastkv_b200 import patch
+    from parity_utils import check_selection
+    sel_layer, topk, n = 1, 96, 700
+    ids = torch.randint(0, 211, (1, n), generator=torch.Generator().manual_seed(5))
+    patch.replace_llama("gemfilter")
+    try:
+        model = _model(torch.bfloat16).to(DEV)
+        patch.set_model(model, _args(method="gemfilter", max_capacity_prompts=topk))
+        pred, cache = patch.gemfilter_generate_selection_prefill(ids.to(DEV), None, model, None, select_layer_idx=sel_layer)
+        torch.cuda.synchronize()
+        attn = model.model.layers[sel_layer].self_attn
+        got = attn.indecies
+        assert got.shape == (1, 1, topk) and all(layer.self_attn.select_mode is False for layer in model.model.layers)
+        assert len(model.model.layers) == 3 and cache.get_seq_length() == topk and pred.shape == (1, 1)
+        # oracle on the q/k the selection layer saw (hidden state entering it, its own projections + RoPE)
+        with torch.no_grad():
+            hs = model.model(ids.to(DEV), output_hidden_states=True, use_cache=False).hidden_states[sel_layer]
+            x = model.model.layers[sel_layer].input_layernorm(hs)
+            q = attn.q_proj(x).view(1, n, -1, 64).transpose(1, 2)
+            k = attn.k_proj(x).view(1, n, -1, 64).transpose(1, 2)
+            pos = torch.arange(n, device=DEV)[None]
+            cos, sin = model.model.rotary_emb(x, pos)
+            q, k = apply_rotary_pos_emb(q, k, cos, sin)
+        ref_scores, ref_idx, _ = O.gemfilter_select(q.float().cpu(), k.float().cpu(), q.shape[1] // k.shape[1], topk)
+        check_selection(ref_scores[0], ref_idx[0], got[0].cpu(), "gemfilter driver")
+        # pass 2 ran on the selected tokens in original order
+        new_ids = patch.get_layer_context(model, None, ids[0].to(DEV), sel_layer)
+        assert torch.equal(new_ids[0].cpu(), ids[0][got[0, 0].sort().values.cpu()])
+        out_ids = patch.gemfilter_generate(model, None, pred, cache, max_gen_len=4)
+        assert len(out_ids) == 5 and cache.get_seq_length() == topk + 4
+    finally:
+        patch.replace_llama("fullkv")

@@ -97,3 +97,39 @@ def test_compact_cache_update_contract():
         c.update(k1, v1, 0)
     with pytest.raises(RuntimeError):
         c.update(k1, v1, 0)
+
+
+def test_gemfilter_patch_plumbing():
+    """baselines/gemfilter: attention attributes, set_topk via set_model, layer truncation for the selection pass,
+    and the stock path when select_mode is off (no kernels involved on CPU)."""
+    from fastkv_b200 import patch
+    patch.replace_llama("gemfilter")
+    try:
+        model = _tiny_llama(3)
+        attn = model.model.layers[0].self_attn
+        assert (attn.topk, attn.select_layer_idx, attn.select_mode, attn.indecies) == (1024, 13, False, None)   # llama_model.py:88-98
+        patch.set_model(model, _args(method="gemfilter", max_capacity_prompts=40, retain_rate=0.3, eviction_mode="proportional"))
+        assert all(l.self_attn.topk == 40 and l.self_attn.retain_rate == 0.3 and l.self_attn.eviction_mode == "proportional"
+                   for l in model.model.layers)                                                                # utils.py:78-89
+        assert patch.set_select_layer(model, 1) == 1 and all(l.self_attn.select_layer_idx == 1 for l in model.model.layers)
+        m2, orig = patch.reduce_layer(model, 1)
+        assert len(m2.model.layers) == 2
+        patch.recover_layer(model, orig)
+        assert len(model.model.layers) == 3
+        # select mode off: identical to the stock model
+        ids = torch.randint(0, 97, (1, 20), generator=torch.Generator().manual_seed(1))
+        with torch.no_grad():
+            got = model(ids, use_cache=True).logits
+        patch.replace_llama("fullkv")
+        with torch.no_grad():
+            ref = model(ids, use_cache=True).logits
+        assert torch.allclose(got, ref, atol=1e-5)
+        # the selection itself needs the CUDA library: no CPU fallback
+        patch.replace_llama("gemfilter")
+        patch.set_select_mode(model, True)
+        patch.set_select_layer(model, 0)
+        with pytest.raises(RuntimeError):
+            with torch.no_grad():
+                model(ids, use_cache=False)
+    finally:
+        patch.replace_llama("fullkv")
