@@ -158,3 +158,37 @@ def test_gemfilter_two_pass_driver_selects_like_the_oracle():
         assert len(out_ids) == 5 and cache.get_seq_length() == topk + 4
     finally:
         patch.replace_llama("fullkv")
+
+
+def test_proportional_preset_end_to_end(patched):
+    """The reference's canonical preset (scripts/eval_e2e.sh: eviction_mode=proportional, retain_rate, tsp_rate;
+    SURVEY.md §8f rank 3) through set_model + a patched prefill: every layer keeps int(q_len * rate) rows with
+    the per-layer rate of compress_fastkv (utils.py:43-46, :86-87, :123-124), the TSP layer keeps
+    int(L * tsp_rate) tokens, and the selected sets are the glue oracle's."""
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    n, retain, tsp_rate, tsp_idx = 640, 0.1, 0.25, 1
+    model = _model(torch.float32)
+    ids = torch.randint(0, 211, (1, n), generator=torch.Generator().manual_seed(9))
+    knobs = [dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=(i == tsp_idx),
+                  tsp_length=256, tsp_rate=tsp_rate, eviction_mode="proportional",
+                  retain_rate=retain if i <= tsp_idx else retain / tsp_rate) for i in range(3)]
+    patched.replace_llama("fullkv")
+    _, ref_caches, traces = G.fastkv_prefill(model, ids, knobs, apply_rotary_pos_emb)
+    patched.replace_llama("fastkv")
+    gm = _model(torch.float32).to(DEV)
+    patched.set_model(gm, _args(eviction_mode="proportional", retain_rate=retain, tsp_rate=tsp_rate, tsp_idx=tsp_idx))
+    for layer in gm.model.layers:
+        layer.self_attn.kv_cluster.keep_aux = True
+    with torch.no_grad():
+        out = gm.model(ids.to(DEV), use_cache=True)
+    torch.cuda.synchronize()
+    cache = out.past_key_values
+    t = int(n * tsp_rate)                                           # tokens propagated past the TSP layer
+    expect = [int(n * retain), int(n * retain), int(t * (retain / tsp_rate))]
+    for i in range(3):
+        assert cache.buffers(i)[2] == expect[i] == ref_caches[i][0].shape[2]
+        cl = gm.model.layers[i].self_attn.kv_cluster
+        assert cl.max_capacity_prompt == expect[i]                  # the attribute is rewritten like the reference's
+    tsp = gm.model.layers[tsp_idx].self_attn.tsp_idx
+    assert tsp.shape == (1, t) and gm.model.layers[tsp_idx].self_attn.kv_cluster.tsp_length == t
+    assert O.near_tie_set_mismatch(traces[tsp_idx].importance[0], ref_caches[tsp_idx][2][0, :-8], tsp[0, :-8].cpu()) == 0
