@@ -40,6 +40,9 @@ class FastKVCluster:
         self.shard = None                       # fastkv_b200.dist.HeadShard for KV-head-sharded runs
         self.keep_aux = False                   # keep scores / indices of the last call in self.last_aux
         self.last_aux = None
+        # optional callable (batch, kv_heads, rows, head_dim, dtype, device) -> (k_buf, v_buf) [B,Hkv,rows,D] views:
+        # the compaction kernel then writes straight into the caller's cache slot
+        self.out_provider = None
 
     def reset(self, window_size=8, max_capacity_prompt=512, kernel_size=7, pooling='avgpool', tsp_layer=False,
               tsp_length=2048, tsp_rate=0.25, retain_rate=0.25, eviction_mode="constant"):
@@ -99,10 +102,15 @@ class FastKVCluster:
         if self.shard is not None and self.shard.world_size > 1 and want_tsp:
             k, v, tsp = self._update_kv_sharded(key_states, query_states, value_states)
         else:
+            k_dst = v_dst = None
+            if self.out_provider is not None and not host_io:
+                k_dst, v_dst = self.out_provider(bsz, key_states.shape[1], self.max_capacity_prompt, head_dim,
+                                                 key_states.dtype, key_states.device)
             res = ops.compress(query_states, key_states, value_states, window_size=self.window_size,
                                kernel_size=self.kernel_size, pooling=self.pooling,
                                capacity=self.max_capacity_prompt, tsp_len=self.tsp_length if want_tsp else 0,
-                               mode=L.MODE_FASTKV, impl=self.score_impl, return_aux=self.keep_aux)
+                               mode=L.MODE_FASTKV, impl=self.score_impl, return_aux=self.keep_aux,
+                               k_out=k_dst, v_out=v_dst)
             k, v, tsp = res[0], res[1], res[2]
             if self.keep_aux:
                 self.last_aux = res[3]

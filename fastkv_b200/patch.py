@@ -143,8 +143,14 @@ def _make_forwards(mod, method, sliding_window_attr=False):
                 if not hasattr(self, "kv_cluster"):
                     init_fastkv(self) if method == "fastkv" else init_snapkv(self)
                 if method == "fastkv":
+                    if isinstance(past_key_values, CompactKVCache):
+                        # the compaction kernel writes straight into this layer's slot of the pre-allocated cache
+                        cache, li = past_key_values, self.layer_idx
+                        self.kv_cluster.out_provider = lambda b, h, rows, d, dt, dev: tuple(
+                            buf[:, :, :rows] for buf in cache.reserve(li, b, h, rows, d, dt, dev))
                     k_c, v_c, self.tsp_idx = self.kv_cluster.update_kv(
                         key_states, query_states, value_states, attention_mask, self.num_key_value_groups, self.layer_idx)
+                    self.kv_cluster.out_provider = None
                 else:
                     k_c, v_c = self.kv_cluster.update_kv(
                         key_states, query_states, value_states, attention_mask, self.num_key_value_groups)
