@@ -1112,9 +1112,9 @@ small_compress_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_con
 #pragma unroll
     for (int w8 = 1; w8 < kSfThreads / 32; ++w8) { lo = min(lo, wtot[w8]); hi = max(hi, wtot[32 + w8]); }
     SF_TRACE(12);
-    const unsigned long long range = (unsigned long long)(hi - lo) + 1ull;
-    const unsigned long long mult = ((4096ull << 32) - 1ull) / range;
-    auto rbin = [&](uint32_t key) { return 4095u - min(4095u, (uint32_t)(((unsigned long long)(key - lo) * mult) >> 32)); };   // 0 = largest keys
+    const int range_bits = 32 - __clz(hi - lo);       // bin = (key - lo) >> shift < 4096 (2048..4096 bins in use)
+    const int bin_shift = range_bits > 12 ? range_bits - 12 : 0;
+    auto rbin = [&](uint32_t key) { return 4095u - ((key - lo) >> bin_shift); };   // 0 = largest keys
     for (int i0 = tid; i0 < n; i0 += kSfThreads * UB) {
       uint32_t bn[UB];
 #pragma unroll

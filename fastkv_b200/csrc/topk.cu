@@ -499,6 +499,15 @@ topk_cluster_kernel(TopkArgs a) {
     return;
   }
 
+  // the leader's adaptive-bin counters (sm.hist is free from here on) are zeroed now, behind the candidate traffic
+  const uint32_t klo = thr;
+  const uint32_t khi = (sm.bc[6] << 20) | 0xfffffu;                     // upper bound of the top non-empty 12-bit bin
+  // bin = (key - klo) >> bin_shift < 4096: a power-of-two map of the candidates' key range (2048..4096 bins in use)
+  const int range_bits = 32 - __clz(khi - klo);
+  const int bin_shift = range_bits > 12 ? range_bits - 12 : 0;
+  if (crank == 0)
+    for (int i = tid; i < kMaxBins; i += kThreads) sm.hist[i] = 0;
+
   // ---- 3. send candidates (bin >= bin*) to the leader: count, one cursor atomic per warp, write ------
   {
     uint32_t mine = 0;
@@ -532,15 +541,11 @@ topk_cluster_kernel(TopkArgs a) {
     uint32_t* cursor = sm.hist;
     uint16_t* bbase = sm.bbase;
     unsigned long long* grouped = sm.sortbuf;
-    const uint32_t klo = thr;
-    const uint32_t khi = (sm.bc[6] << 20) | 0xfffffu;                   // upper bound of the top non-empty 12-bit bin
-    const unsigned long long range = (unsigned long long)(khi - klo) + 1ull;
-    const unsigned long long mult = (((unsigned long long)kMaxBins << 32) - 1ull) / range;   // bin = ((key-klo)*mult) >> 32 < 4096
-    auto fine_bin = [&](uint32_t key) { return (uint32_t)(((unsigned long long)(key - klo) * mult) >> 32); };
-    for (int i = tid; i < kMaxBins; i += kThreads) cursor[i] = 0;
-    __syncthreads();
+    auto fine_bin = [&](uint32_t key) { return (key - klo) >> bin_shift; };
+    TK_TRACE(8);
     for (int i = tid; i < (int)n_cand; i += kThreads) atomicAdd(&cursor[fine_bin((uint32_t)(sm.cand[i] >> 32))], 1u);
     __syncthreads();
+    TK_TRACE(9);
     bool skew;
     {
       uint32_t local[4], ls = 0, mx = 0;
@@ -559,6 +564,7 @@ topk_cluster_kernel(TopkArgs a) {
       }
     }
     __syncthreads();
+    TK_TRACE(10);
     unsigned long long kth = 0ull;
     if (!skew) {
       for (int i = tid; i < (int)n_cand; i += kThreads) {
@@ -567,6 +573,7 @@ topk_cluster_kernel(TopkArgs a) {
         grouped[bbase[b] + atomicAdd(&cursor[b], 1u)] = c;
       }
       __syncthreads();
+      TK_TRACE(11);
       for (int i = tid; i < (int)n_cand; i += kThreads) {
         const unsigned long long c = grouped[i];
         const uint32_t b = fine_bin((uint32_t)(c >> 32));
@@ -768,7 +775,7 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
       unsigned long long h[16];
       cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[topk trace] n=%d rows=%d C=%d order=%d:", p.n, p.rows, Cp, p.order);
-      for (int i = 1; i <= 7; ++i) fprintf(stderr, " %d:%.2f", i, (double)(h[i] - h[0]) / 1e3);
+      for (int i = 1; i <= 11; ++i) fprintf(stderr, " %d:%.2f", i, (double)(h[i] - h[0]) / 1e3);
       fprintf(stderr, "\n");
     }
     return FKV_OK;
