@@ -599,11 +599,14 @@ topk_cluster_kernel(TopkArgs a) {
     }
     if (by_value) {
       for (int i = tid; i < a.tail; i += kThreads) out[k + i] = (int64_t)(n + i);
-    } else if (tid == 0) {
-      for (int cc = 0; cc < C; ++cc) {
-        uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, cc) : sm.bc;
-        rbc[4] = (uint32_t)(kth & 0xffffffffull);
-        rbc[5] = (uint32_t)(kth >> 32);
+    } else {
+      __syncthreads();                              // every thread has read bc[4..5] before they are rewritten
+      if (tid == 0) {
+        for (int cc = 0; cc < C; ++cc) {
+          uint32_t* rbc = multi ? cluster.map_shared_rank(sm.bc, cc) : sm.bc;
+          rbc[4] = (uint32_t)(kth & 0xffffffffull);
+          rbc[5] = (uint32_t)(kth >> 32);
+        }
       }
     }
   }
