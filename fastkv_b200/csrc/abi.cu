@@ -255,6 +255,9 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
     tt.imp_out = p->imp_out;
     tt.workspace = ws + score_ws + head_ws; tt.workspace_bytes = tsp_ws;
     if ((rc = launch_topk(tt, s)) != FKV_OK) return rc;
+    if (p->imp_out && Hsel == 1)                     // a single selection head: the importance IS its score row
+      FKV_CUDA_TRY(cudaMemcpy2DAsync(p->imp_out, (size_t)P * sizeof(float), sp.score, (size_t)sp.score_stride_b * sizeof(float),
+                                     (size_t)P * sizeof(float), sp.B, cudaMemcpyDeviceToDevice, s));
   }
   return fused ? FKV_OK : launch_gather_kv(g, s);
 }
