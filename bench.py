@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the 32k / 128k single-call extra")
     ap.add_argument("--no-model", action="store_true")
     ap.add_argument("--score-impl", default="auto", choices=["auto", "simple", "tensor"])
     return ap.parse_args()
@@ -404,6 +405,44 @@ def run_ours(args):
                 "kernels_per_call": int(score_kernels), "us_per_call": round(score_us, 2),
                 "algorithmic_bytes_per_call": sbytes, "peak_source": peak_src}
 
+    # ---- extra: one update_kv call (score -> top-k -> compaction) and its scoring stage at 32k and 128k,
+    # the two ends of the north star's range; graph replay over rotating inputs, rank 0 at N = 1 only
+    context_sweep = None
+    if world == 1 and not args.no_sweep:
+        context_sweep = []
+        for sl in (32768, 131072):
+            try:
+                nb_ = 3 if sl <= 32768 else 2
+                bufs_ = [(rand(1, sl, HQ), rand(1, sl, HKV), rand(1, sl, HKV)) for _ in range(nb_)]
+                rec = {"ctx": sl}
+                for name, fn in (("pipeline_us", lambda q, k, v: ops.compress(q, k, v, window_size=W, kernel_size=KS, pooling=POOL, capacity=args.capacity)),
+                                 ("score_us", lambda q, k, v: ops.score(q, k, window_size=W, kernel_size=KS, pooling=POOL))):
+                    for x in bufs_:
+                        fn(*x)
+                    torch.cuda.synchronize()
+                    g_ = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g_):
+                        for x in bufs_:
+                            fn(*x)
+                    g_.replay()
+                    torch.cuda.synchronize()
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    for _ in range(10):
+                        g_.replay()
+                    a1.record()
+                    torch.cuda.synchronize()
+                    rec[name] = round(a0.elapsed_time(a1) * 1e3 / (10 * nb_), 2)
+                    del g_
+                pb_, sb_ = layer_bytes(1, HKV, HQ, sl, args.capacity, 0), score_stage_bytes(1, HKV, HQ, sl)
+                rec.update({"pipeline_algorithmic_bytes": pb_, "pipeline_frac": round(pb_ / (rec["pipeline_us"] * 1e-6) / 1e9 / peak, 4),
+                            "score_algorithmic_bytes": sb_, "score_frac": round(sb_ / (rec["score_us"] * 1e-6) / 1e9 / peak, 4)})
+                context_sweep.append(rec)
+                del bufs_
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                context_sweep.append({"ctx": sl, "error": f"{type(e).__name__}: {e}"})
+
     # ---- e2e: FastKVCluster.update_kv on pinned HOST buffers -----------------------------------
     e2e = None
     if not args.no_e2e:
@@ -488,7 +527,7 @@ def run_ours(args):
             "timed_with": timed_with,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu, "model": model_extras,
+            "roofline": roofline, "cpu_baseline": cpu, "context_sweep": context_sweep, "model": model_extras,
         }
         print(json.dumps(line))
     if world > 1:
