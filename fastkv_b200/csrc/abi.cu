@@ -119,6 +119,9 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
   if (!workspace || workspace_bytes < 256) return FKV_EWORKSPACE;
   FKV_CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  // header word 4 = "initialised" mark; the scoring kernel traps on a workspace that never went through here
+  static const uint32_t magic = kWorkspaceMagic;
+  FKV_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(workspace) + 16, &magic, sizeof(magic), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return FKV_OK;
 }
 

@@ -34,6 +34,8 @@ __host__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a
 
 inline int dtype_size(int dtype) { return dtype == FKV_F32 ? 4 : 2; }
 
+constexpr uint32_t kWorkspaceMagic = 0xF457CB20u;   // written at byte 16 of a workspace by fkv_workspace_init
+
 void count_launch();   // bumps the process-wide kernel-launch counter (abi.cu)
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------

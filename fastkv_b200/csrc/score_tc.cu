@@ -367,6 +367,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     float mn[N], z[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+    // a workspace that never went through fkv_workspace_init has a garbage departure counter / epoch and would
+    // make stale records look valid: fail loudly instead of computing on them
+    if (et == 0 && blockIdx.x == 0 && __ldcg(a.sync_counter + 4) != kWorkspaceMagic) {
+      printf("fastkv_b200: fkv_score got a workspace that was not passed through fkv_workspace_init\n");
+      __trap();
+    }
     // launch epoch (bumped by the last CTA of every launch) -> the two record tags of this launch
     const unsigned long long epoch = __ldcg(reinterpret_cast<const unsigned long long*>(a.sync_counter + 2)) + 1ull;
     const unsigned int tag_m = 0x7fc00000u | (unsigned)(epoch & 0x3fffffu);

@@ -212,6 +212,7 @@ int fkv_compress(const fkv_compress_params* p, void* stream);
 /* A workspace must be passed through fkv_workspace_init ONCE after allocation: it zeroes the buffer,
  * i.e. the 256-byte header (departure counter + launch epoch of the scoring kernel) and the region
  * where CTAs exchange epoch-tagged partial softmax statistics.  Calls keep the header consistent.
+ * (fkv_score traps with a device-side message when the workspace never went through fkv_workspace_init.)
  * The header is persistent state of fkv_score / fkv_compress: do not pass the same pointer as the
  * scratch of fkv_topk / fkv_decode_attn (offset it by 256 bytes, or use a separate buffer). */
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream);

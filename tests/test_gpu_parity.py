@@ -283,6 +283,31 @@ def test_scratch_users_leave_the_scoring_header_alone():
         assert torch.equal(aux0["score"], aux1["score"])
 
 
+_UNINIT_WS = r"""
+import sys, torch
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+from fastkv_b200 import ops, _lib as L
+from parity_utils import make_inputs
+buf = torch.full((1 << 24,), 0xAB, dtype=torch.uint8, device="cuda")      # never passed through fkv_workspace_init
+L.workspace = lambda device, nbytes: buf
+q, k, v = [x.cuda().bfloat16() for x in make_inputs(1, 1, 8, 2, 2000, 128)]
+try:
+    ops.score(q, k, window_size=8, kernel_size=7, impl=L.IMPL_TENSOR)
+    torch.cuda.synchronize()
+    print("NO ERROR")
+except Exception as e:
+    print("FAILED LOUDLY:", type(e).__name__)
+"""
+
+
+def test_uninitialised_workspace_fails_loudly():
+    """fkv_score on a workspace that skipped fkv_workspace_init must not compute on garbage header state."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", _UNINIT_WS, root], capture_output=True, text=True, timeout=170)
+    assert "FAILED LOUDLY" in r.stdout and "NO ERROR" not in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+
+
 def test_strided_blhd_views_equal_contiguous_inputs():
     """update_kv gets [B,H,L,D] views of [B,L,H,D] memory; results must not depend on the layout."""
     knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)
