@@ -1,20 +1,25 @@
-// K1/K2 tensor-core path: fused observation-window scoring + pooling + GQA group-sum for 16-bit
-// inputs, hand-written for sm_100a (TMA -> shared memory -> tcgen05.mma -> TMEM -> registers).
-// Replaces baselines/fastkv/utils.py:93-112 (and the SnapKV twin) with ONE persistent kernel.
+// K1/K2 tensor-core paths, hand-written for sm_100a (TMA -> shared memory -> tcgen05.mma -> TMEM -> registers):
+//   score_tc_kernel        observation-window scoring + pooling + GQA group-sum (baselines/fastkv/utils.py:93-112
+//                          and the SnapKV twin), one persistent cooperative kernel that reads K exactly once
+//   gemfilter_tc_kernel    GemFilter selection scores (baselines/gemfilter/utils.py:25-33), single pass
+//   small_compress_kernel  opt-in: the whole update_kv chain of a short-context layer in one cluster kernel
 //
+// score_tc_kernel
 // Work unit  = (batch b, kv head h, key tile t).  A tile is 128 consecutive key rows (UMMA M) that
 //              start `half = kernel_size/2` rows before the S = 128 - 2*half keys it OWNS, so the
 //              pooling halo is recomputed instead of exchanged between CTAs.
-// MMA        = logits[128 keys x N] = K_tile[128 x D] . Qwin[N x D]^T, N = G*W window-rows of the
-//              G query heads of that kv head, bf16/f16 operands, fp32 accumulators in TMEM.
-// Two passes over the CTA's contiguous unit range, separated by one grid-wide barrier:
-//   pass 1   per row (max, sum exp2) over the owned keys (lazy per-warp rescaling), flushed per
-//            (b, h) pair to global partials
-//   pass 2   (tiles in reverse order: the most recently streamed K is still in L2)
-//            p = exp2(x - max) / sum  ->  votes per query head  ->  pool1d over the halo'd tile
-//            -> group-sum  ->  score[b, h, j]
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator,
-// warps 2-5 / 6-9 = two epilogue warpgroups that alternate tiles (double-buffered accumulators).
+// MMA        = logits[128 keys x N] = K_tile[128 x D] . Qwin[N x D]^T, N = G*W <= 32 window-rows of the
+//              query heads of that kv head (wider groups: one launch per head sub-group), bf16/f16
+//              operands, fp32 accumulators in TMEM.  All 512 TMEM columns are a cache of NB = 512/N logit tiles.
+// Phases     = the (b, h) pairs are processed in groups whose tiles fit that cache on every CTA, so the
+//              logits of a tile stay on chip between its two passes:
+//   pass 1   per row (max, sum exp2) over the owned keys (lazy per-warp rescaling), flushed per (b, h)
+//            pair as epoch-tagged records; a CTA then assembles the final statistics of its pairs from the
+//            records of the CTAs that share them (no grid barrier: records validate themselves)
+//   pass 2   p = exp2(x - max) / sum from the logits in TMEM -> votes per query head -> pool1d over the
+//            halo'd tile -> group-sum -> score[b, h, j]; reading a tile frees its TMEM block for the next phase
+// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (both stream
+// through all phases without stopping), warps 2-13 = three epilogue warpgroups taking tiles round-robin.
 #include <cuda.h>
 #include <cooperative_groups.h>
 
