@@ -186,7 +186,9 @@ __device__ __forceinline__ float warp_max_f32(float v) {
   return r;
 }
 
-template <int W, int G>
+// kDef: the reference's default epilogue (avgpool, kernel_size 7, FastKV group-sum, single head group) compiled
+// without the other variants, so the pass-2 loop stays small and contiguous in the instruction cache
+template <int W, int G, bool kDef>
 __global__ void __launch_bounds__(kTcThreads, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_q, const TcArgs a) {
   constexpr int N = W * G;                          // logit rows per (b, kv head)
@@ -567,37 +569,50 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
 #pragma unroll
         for (int r = 0; r < W; ++r)                  // rows summed in order (utils.py:104)
           vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mn[g * W + r])), z[g * W + r], vote);
-        vb[g * kTile + row] = in_prefix ? vote : pad;
+        vb[g * kTile + row] = in_prefix ? vote : (kDef ? 0.f : pad);
       }
       named_bar(3 + wg, 128);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
       if (own) {
-        // a later head sub-group continues the sum of the earlier launches: ((p0 + p1) + p2) + p3 as in utils.py:112
-        float acc = a.accumulate ? a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] : 0.f;
+        if constexpr (kDef) {
+          float acc = 0.f;
 #pragma unroll
-        for (int g = 0; g < G; ++g) {
-          float pooled;
-          if (a.pooling == FKV_POOL_MAX) {
-            pooled = -INFINITY;
-            for (int d = -a.half; d <= a.half; ++d) pooled = fmaxf(pooled, vb[g * kTile + row + d]);
-          } else {
-            float sum = 0.f;
+          for (int g = 0; g < G; ++g) {
             const float* vr = vb + g * kTile + row;
-            if (a.half == 3) {                        // kernel_size 7 (the reference default), unrolled
+            float sum = 0.f;
 #pragma unroll
-              for (int d = -3; d <= 3; ++d) sum += vr[d];
-            } else if (a.half == 2) {
-#pragma unroll
-              for (int d = -2; d <= 2; ++d) sum += vr[d];
-            } else {
-              for (int d = -a.half; d <= a.half; ++d) sum += vr[d];
-            }
-            pooled = sum * inv_ks;                    // count_include_pad: always / kernel_size
+            for (int d = -3; d <= 3; ++d) sum += vr[d];
+            acc += sum * inv_ks;                      // avg_pool1d (count_include_pad), GQA group-sum with g in order
           }
-          if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
-          else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * a.q_heads_per_kv + a.g0 + g - a.out_h0) * a.score_sh + key] = pooled;
+          a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
+        } else {
+          // a later head sub-group continues the sum of the earlier launches: ((p0 + p1) + p2) + p3 as in utils.py:112
+          float acc = a.accumulate ? a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] : 0.f;
+  #pragma unroll
+          for (int g = 0; g < G; ++g) {
+            float pooled;
+            if (a.pooling == FKV_POOL_MAX) {
+              pooled = -INFINITY;
+              for (int d = -a.half; d <= a.half; ++d) pooled = fmaxf(pooled, vb[g * kTile + row + d]);
+            } else {
+              float sum = 0.f;
+              const float* vr = vb + g * kTile + row;
+              if (a.half == 3) {                        // kernel_size 7 (the reference default), unrolled
+  #pragma unroll
+                for (int d = -3; d <= 3; ++d) sum += vr[d];
+              } else if (a.half == 2) {
+  #pragma unroll
+                for (int d = -2; d <= 2; ++d) sum += vr[d];
+              } else {
+                for (int d = -a.half; d <= a.half; ++d) sum += vr[d];
+              }
+              pooled = sum * inv_ks;                    // count_include_pad: always / kernel_size
+            }
+            if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
+            else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * a.q_heads_per_kv + a.g0 + g - a.out_h0) * a.score_sh + key] = pooled;
+          }
+          if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
         }
-        if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
       }
       t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
@@ -1386,11 +1401,11 @@ Plan make_plan(const fkv_score_params& p) {
   return pl;
 }
 
-template <int W, int G>
+template <int W, int G, bool kDef>
 int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, int grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tc_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tc_kernel<W, G, kDef>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -1405,7 +1420,7 @@ int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, i
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;             // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
-  FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G>, mk, mq, a));
+  FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G, kDef>, mk, mq, a));
   count_launch();
   return FKV_OK;
 }
@@ -1560,10 +1575,12 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   }
 
   int rc_launch = FKV_EMODE;
-#define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) rc_launch = launch_inst<w, g>(mk, mq, a, pl.grid, pl.smem, s)
+#define FKV_TC_CASE(w, g) if (pl.W == w && pl.G == g) rc_launch = def_epi ? launch_inst<w, g, true>(mk, mq, a, pl.grid, pl.smem, s) \
+                                                                          : launch_inst<w, g, false>(mk, mq, a, pl.grid, pl.smem, s)
   for (int g0 = 0; g0 < pl.Gm; g0 += pl.G) {         // one launch per head sub-group (a single one for W*G <= 32)
     a.g0 = g0;
     a.accumulate = (a.group_sum && g0 > 0) ? 1 : 0;
+    const bool def_epi = a.group_sum && !a.accumulate && a.pooling == FKV_POOL_AVG && a.half == 3;
     FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4);
     FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2);
     FKV_TC_CASE(32, 1);
