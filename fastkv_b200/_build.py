@@ -36,7 +36,10 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("FKV_BUILD_TRACE") == "1":      # compile the %globaltimer phase timelines into the scoring kernel
+        flags.append("-DFKV_TC_TRACING")
+    cmd = [nvcc] + flags + ["-o", LIB] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr
     with open(os.path.join(HERE, "csrc", "build.log"), "w") as f:

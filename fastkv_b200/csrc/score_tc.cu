@@ -141,8 +141,16 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+// Phase timelines (%globaltimer stamps printed by the host side) are a build-time option: python fastkv_b200/_build.py
+// with FKV_BUILD_TRACE=1 compiles them in, FKV_TC_TRACE=1 then prints them.  The default build carries no
+// tracing code: the single-thread TMA / MMA loops pace the pipeline and every instruction in them counts.
+#ifdef FKV_TC_TRACING
 #define FKV_TRACE2(role, m) do { if (a.trace && blockIdx.x == 0 && (m) < 64) a.trace[256 * 16 + (role) * 64 + (m)] = gtimer(); } while (0)
 #define FKV_TRACE(slot) do { if (a.trace) a.trace[(size_t)blockIdx.x * 16 + (slot)] = gtimer(); } while (0)
+#else
+#define FKV_TRACE2(role, m) do { } while (0)
+#define FKV_TRACE(slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ float ex2(float x) {
   float y;

@@ -1,4 +1,5 @@
-"""FKV_TC_TRACE=1 python tools/trace_layout.py <ctx> <layout blhd|bhld>  — phase timeline of the scoring kernel."""
+"""FKV_TC_TRACE=1 python tools/trace_layout.py <ctx> <layout blhd|bhld>  — phase timeline of the scoring kernel.
+Needs a library built with FKV_BUILD_TRACE=1 python fastkv_b200/_build.py (tracing is compiled out by default)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
