@@ -89,7 +89,7 @@ __device__ inline uint32_t block_scan_incl(uint32_t v, uint32_t* wsum, uint32_t&
 }
 
 // ---- generic single-CTA selection over a row in global memory ---------------------------------------
-__device__ void select_row_generic(const float* __restrict__ x, int n, int k, int order, int tail,
+__device__ __noinline__ void select_row_generic(const float* __restrict__ x, int n, int k, int order, int tail,
                                    int64_t* __restrict__ out, uint32_t* hist, uint32_t* wsum, uint32_t* bc,
                                    unsigned long long* comp, int sort_cap) {
   const int tid = threadIdx.x;
