@@ -293,6 +293,9 @@ __device__ inline void bitonic_desc(unsigned long long* buf, int cap) {
 
 #define TK_TRACE(i) do { if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); a.trace[i] = t_; } } while (0)
 
+// kByValue: per-head selection in score order (+ optional fused KV copy); false: the TSP row (index order, head sum).
+// Two instances, so that neither carries the other's code and register pressure (64-register cap at 1024 threads).
+template <bool kByValue>
 __global__ void __launch_bounds__(kThreads, 1)
 topk_cluster_kernel(TopkArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -427,7 +430,7 @@ topk_cluster_kernel(TopkArgs a) {
   uint32_t thr = bin_star << 20;                    // candidates are the keys >= thr
   uint32_t n_above = sm.bc[1];
   uint32_t n_cand = n_above + sm.bc[2];
-  const bool by_value = (a.order == FKV_ORDER_VALUE_DESC);
+  constexpr bool by_value = kByValue;
 
   if (n_cand > (uint32_t)kCandMax) {
     // ---- 2b. crowded threshold bin (narrow score distributions put thousands of keys within one
@@ -613,7 +616,7 @@ topk_cluster_kernel(TopkArgs a) {
   TK_TRACE(5);
   csync();
   TK_TRACE(7);
-  if (by_value) {
+  if constexpr (by_value) {
     if (a.g.enabled) {
       // ---- 4b. fused KV compaction (baselines/fastkv/utils.py:114-121): the whole cluster copies the
       // selected rows of this (batch, head) + the W window rows; indices come from `out` (global,
@@ -749,7 +752,9 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
     a.write_dense = (a.nsum > 1);                   // the fallback inside the kernel needs the dense row
     static bool attr_set = false;
     if (!attr_set) {
-      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)sizeof(ClusterSmem)));
+      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)sizeof(ClusterSmem)));
       attr_set = true;
     }
@@ -771,7 +776,8 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
       if (!trace_buf) FKV_CUDA_TRY(cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long)));
       a.trace = trace_buf;
     }
-    FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, topk_cluster_kernel, a));
+    if (by_value) FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, topk_cluster_kernel<true>, a));
+    else FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, topk_cluster_kernel<false>, a));
     count_launch();
     if (trace_on) {
       cudaStreamSynchronize(s);
