@@ -460,9 +460,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // ---------------- pass 1: per-row softmax statistics over owned keys ----------------------
     int pair, t;
     { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
-    for (int j = wg; j < T; j += kNumWG) {
+    // (one extra trip past the last tile performs the phase's final flush: the flush code, 10 % of the kernel's
+    // instructions, then exists once in the instruction stream)
+    for (int j = wg; ; j += kNumWG) {
       const int blk = (jbase + j) & (NB - 1);
-      flush_upto(pair - pair0);
+      flush_upto(j < T ? pair - pair0 : nlp);
+      if (j >= T) break;
       mbar_wait(bar_tfull(blk), ((jbase + j) / NB) & 1);
       if (et == 0 && jbase + j == 0) FKV_TRACE(2);
       tc_fence_after();
@@ -498,8 +501,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
-    if (et == 0 && ph == nph - 1) FKV_TRACE(3);
-    flush_upto(nlp);
     if (et == 0 && ph == nph - 1) FKV_TRACE(4);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
