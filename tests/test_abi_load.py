@@ -118,3 +118,40 @@ def test_constructor_assert_and_reset_semantics():
     cl = FastKVCluster()
     cl.reset(tsp_length=1024)
     assert cl.tsp_length == 1024          # not the reference's accidental 1-tuple (utils.py:73)
+
+
+_C_CLIENT = r"""
+#include <stdio.h>
+#include <string.h>
+#include "fastkv_b200.h"
+int main(void) {
+  fkv_score_params sp; memset(&sp, 0, sizeof sp);
+  sp.struct_size = (uint32_t)sizeof sp;
+  printf("abi %d\n", fkv_abi_version());
+  printf("ws %zu\n", fkv_workspace_bytes(FKV_MODE_FASTKV, 1, 32, 8, 32768, 8, 2048, 2040));
+  printf("rc %d\n", fkv_score(&sp, NULL));   /* invalid arguments: rejected before anything touches the GPU */
+  return 0;
+}
+"""
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(tmp_path):
+    """include/fastkv_b200.h must be usable from the reference-side FFI of any language: compile a C99 client with
+    -pedantic against it, link the shared library, call the query entry points (no GPU involved)."""
+    import os, shutil, subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    from fastkv_b200 import _lib
+    _lib.load()                                                   # builds the library if needed
+    libdir = os.path.join(root, "fastkv_b200")
+    src = tmp_path / "client.c"
+    src.write_text(_C_CLIENT)
+    exe = tmp_path / "client"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), str(src),
+                        "-o", str(exe), "-L", libdir, "-l:libfastkv_b200.so", "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
+    assert int(lines["abi"]) == _lib.load().fkv_abi_version() and int(lines["ws"]) > 0 and int(lines["rc"]) < 0

@@ -133,3 +133,18 @@ def test_gemfilter_patch_plumbing():
                 model(ids, use_cache=False)
     finally:
         patch.replace_llama("fullkv")
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference (the oracle port on host cores) prints the contract's JSON line without a GPU."""
+    import json, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "cpu_baseline"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"]
