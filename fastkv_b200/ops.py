@@ -106,10 +106,11 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, *, window_siz
     if idx.dtype != torch.int64 or idx.stride(2) != 1:
         raise ValueError("fastkv_b200: idx must be int64 with contiguous last dim")
     Cc = n_sel + window_size
+    # sources may be page-locked host tensors (zero-copy reads); the outputs always live on the GPU that runs the kernel
     if k_out is None:
-        k_out = torch.empty((B, Hsel, Cc, D), dtype=k.dtype, device=k.device)
+        k_out = torch.empty((B, Hsel, Cc, D), dtype=k.dtype, device=idx.device)
     if v_out is None:
-        v_out = torch.empty((B, Hsel, Cc, D), dtype=v.dtype, device=v.device)
+        v_out = torch.empty((B, Hsel, Cc, D), dtype=v.dtype, device=idx.device)
     p = L.GatherKvParams()
     p.struct_size = C.sizeof(L.GatherKvParams)
     p.dtype, p.B, p.L, p.D = L.dtype_code(k.dtype), B, Lk, D

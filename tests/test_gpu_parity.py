@@ -504,6 +504,19 @@ def test_host_buffer_path_matches_device_path():
         assert not x.is_cuda and torch.equal(x, y.cpu())
 
 
+def test_gather_kv_reads_pinned_host_sources_zero_copy():
+    """K/V gather sources may be page-locked host tensors (only the selected rows cross PCIe); outputs are on the GPU."""
+    from fastkv_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    k = torch.randn(2, 700, 4, 128, generator=g).bfloat16().pin_memory().transpose(1, 2)
+    v = torch.randn(2, 700, 4, 128, generator=g).bfloat16().pin_memory().transpose(1, 2)
+    idx = torch.stack([torch.stack([torch.randperm(692, generator=g)[:100] for _ in range(4)]) for _ in range(2)]).to(DEV)
+    ko, vo = ops.gather_kv(k.to(DEV), v, idx, window_size=8)
+    kr, vr = ops.gather_kv(k.to(DEV), v.to(DEV), idx, window_size=8)
+    torch.cuda.synchronize()
+    assert ko.is_cuda and vo.is_cuda and torch.equal(ko, kr) and torch.equal(vo, vr)
+
+
 def test_bad_pooling_raises_like_the_reference():
     from fastkv_b200 import FastKVCluster
     q, k, v = [x.to(DEV) for x in make_inputs(1, 1, 8, 2, 256, 128)]
