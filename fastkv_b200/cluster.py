@@ -8,7 +8,6 @@ CUDA kernels behind ``fastkv_b200.ops``; there is no torch or CPU fallback.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 
