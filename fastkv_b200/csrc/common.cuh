@@ -136,6 +136,8 @@ namespace fkv {
 int launch_score_simple(const fkv_score_params& p, cudaStream_t s);
 int launch_score_tensor(const fkv_score_params& p, cudaStream_t s);
 bool score_tensor_supported(const fkv_score_params& p);
+bool gemfilter_tensor_supported(const fkv_score_params& p);     // gemfilter_tc.cu
+int launch_score_gemfilter(const fkv_score_params& p, cudaStream_t s);
 bool small_compress_supported(const fkv_compress_params& p);   // short contexts: one cluster kernel for the whole chain
 int launch_small_compress(const fkv_compress_params& p, cudaStream_t s);
 size_t score_workspace_bytes(int mode, int B, int Hq, int Hkv, int L, int W);

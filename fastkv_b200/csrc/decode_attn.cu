@@ -12,7 +12,6 @@ namespace {
 
 constexpr int kDecThreads = 128;
 constexpr int kDecWarps = kDecThreads / 32;
-constexpr int kMaxGroup = 8;
 
 struct DecodeArgs {
   const void* q; int64_t q_sb, q_sh;
