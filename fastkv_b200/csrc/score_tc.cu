@@ -1,8 +1,7 @@
-// K1/K2 tensor-core paths, hand-written for sm_100a (TMA -> shared memory -> tcgen05.mma -> TMEM -> registers):
-//   score_tc_kernel        observation-window scoring + pooling + GQA group-sum (baselines/fastkv/utils.py:93-112
-//                          and the SnapKV twin), one persistent cooperative kernel that reads K exactly once
-//   gemfilter_tc_kernel    GemFilter selection scores (baselines/gemfilter/utils.py:25-33), single pass
-//   small_compress_kernel  opt-in: the whole update_kv chain of a short-context layer in one cluster kernel
+// K1/K2 tensor-core path, hand-written for sm_100a (TMA -> shared memory -> tcgen05.mma -> TMEM -> registers):
+// observation-window scoring + pooling + GQA group-sum (baselines/fastkv/utils.py:93-112 and the SnapKV twin) as one
+// persistent cooperative kernel that reads K exactly once.  Sibling kernels on the same plumbing (tc_common.cuh):
+// gemfilter_tc.cu (GemFilter scores, single pass) and small_compress.cu (opt-in one-kernel short-context path).
 //
 // score_tc_kernel
 // Work unit  = (batch b, kv head h, key tile t).  A tile is 128 consecutive key rows (UMMA M) that
