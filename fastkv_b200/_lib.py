@@ -14,7 +14,7 @@ import torch
 from . import _build
 
 # ---- enums (mirror include/fastkv_b200.h) -----------------------------------------------------
-ABI_VERSION = 3
+ABI_VERSION = 4
 BF16, F16, F32 = 0, 1, 2
 POOL_AVG, POOL_MAX = 0, 1
 MODE_FASTKV, MODE_SNAPKV, MODE_GEMFILTER = 0, 1, 2
@@ -110,7 +110,8 @@ class CompressParams(C.Structure):
 
 
 EXPORTS = [
-    "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
+    "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_workspace_status",
+    "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
     "fkv_score_impl_name", "fkv_launch_count",
     "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append", "fkv_compress",
 ]
@@ -140,6 +141,8 @@ def load():
         lib.fkv_workspace_bytes.argtypes = [C.c_int32] * 8
         lib.fkv_workspace_init.restype = C.c_int
         lib.fkv_workspace_init.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        lib.fkv_workspace_status.restype = C.c_int
+        lib.fkv_workspace_status.argtypes = [C.c_void_p, C.c_void_p]
         lib.fkv_topk_workspace_bytes.restype = C.c_size_t
         lib.fkv_topk_workspace_bytes.argtypes = [C.c_int32] * 3
         lib.fkv_decode_workspace_bytes.restype = C.c_size_t
@@ -226,11 +229,18 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     return buf
 
 
-WS_HEADER = 256   # fkv_score / fkv_compress keep the scoring kernel's departure counter + launch epoch here
+WS_HEADER = 256   # FKV_WORKSPACE_HEADER_BYTES: the scoring kernel's departure counter + launch epoch + error word
 
 
 def scratch(device: torch.device, nbytes: int):
-    """(ptr, bytes) of the shared buffer PAST the scoring header, for entry points that use their
-    workspace as plain scratch (fkv_topk, fkv_decode_attn): they must not overwrite that header."""
-    buf = workspace(device, nbytes + WS_HEADER)
-    return buf.data_ptr() + WS_HEADER, buf.numel() - WS_HEADER
+    """(ptr, bytes) of the shared per-stream buffer for the entry points that use their workspace as plain scratch
+    (fkv_topk, fkv_decode_attn).  The library itself starts past the scoring header (ABI 4), so the same pointer
+    serves every entry point; ``nbytes`` comes from the *_workspace_bytes queries, which include the header."""
+    buf = workspace(device, nbytes)
+    return buf.data_ptr(), buf.numel()
+
+
+def workspace_status(device: torch.device) -> int:
+    """fkv_workspace_status of the current stream's buffer (synchronises; debugging / tests)."""
+    buf = workspace(device, WS_HEADER)
+    return load().fkv_workspace_status(buf.data_ptr(), torch.cuda.current_stream(device).cuda_stream)

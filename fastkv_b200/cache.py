@@ -31,7 +31,9 @@ class CompactKVCache:
         self.v: List[Optional[torch.Tensor]] = []
         self.seq_lens: List[int] = []                 # host mirror of the per-layer length
         self.seq_lens_dev: List[Optional[torch.Tensor]] = []   # int32 [1] on device (CUDA-graph friendly)
-        self.true_length = 0                           # prompt length + generated tokens (not compacted)
+        self.true_length = 0                           # tokens the model has seen (prompt + generated), NOT the compact
+                                                       # row count: the generate() path continues positions from here
+                                                       # (baselines/monkeypatch.py:280-288)
         self.device_lengths = False                    # True: decode steps advance the device-side lengths only
 
     # -- HF Cache surface -----------------------------------------------------------------------
@@ -46,6 +48,10 @@ class CompactKVCache:
     def get_mask_sizes(self, cache_position=None, layer_idx: int = 0):   # transformers >= 4.5x mask helpers
         q = int(cache_position.shape[0]) if cache_position is not None else 1
         return self.get_seq_length(layer_idx) + q, 0
+
+    def note_tokens(self, n: int):
+        """Called once per model forward with the number of new tokens (prompt length, then 1 per decode step)."""
+        self.true_length += int(n)
 
     def _grow_lists(self, layer_idx: int):
         while len(self.k) <= layer_idx:
@@ -79,10 +85,11 @@ class CompactKVCache:
                 kbuf[:, :, :rows].copy_(key_states)
                 vbuf[:, :, :rows].copy_(value_states)
             self.set_length(layer_idx, rows)
-            if layer_idx == 0:
-                self.true_length = max(self.true_length, rows)
         else:
             kbuf, vbuf = self.k[layer_idx], self.v[layer_idx]
+            if h != kbuf.shape[1] or b != kbuf.shape[0] or d != kbuf.shape[3]:
+                raise ValueError(f"CompactKVCache.update: new row has shape {tuple(key_states.shape)} but layer {layer_idx} caches "
+                                 f"{tuple(kbuf.shape)} (SnapKV caches hold one head per QUERY head: expand K/V first)")
             n = self.seq_lens[layer_idx]
             if n >= kbuf.shape[2]:
                 raise RuntimeError("CompactKVCache is full: raise max_new_tokens")
@@ -93,8 +100,6 @@ class CompactKVCache:
                 vbuf[:, :, n] = value_states[:, :, 0]
             self.seq_lens[layer_idx] = n + 1
             self.seq_lens_dev[layer_idx].add_(1)
-            if layer_idx == 0:
-                self.true_length += 1
         n = self.seq_lens[layer_idx]
         return self.k[layer_idx][:, :, :n], self.v[layer_idx][:, :, :n]
 

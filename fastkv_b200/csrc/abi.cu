@@ -2,6 +2,9 @@
 // No torch headers, no allocation, no synchronisation (see include/fastkv_b200.h).
 #include <atomic>
 #include <cstring>
+#include <mutex>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -10,18 +13,67 @@ namespace fkv {
 static std::atomic<unsigned long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+constexpr int kMaxDevices = 64;
+
+static int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+  return dev;
+}
+
 int num_sms() {
-  static std::atomic<int> cached{0};
-  int v = cached.load(std::memory_order_relaxed);
-  if (v > 0) return v;
-  int dev = 0, sms = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess ||
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+  static std::atomic<int> cached[kMaxDevices];          // zero-initialised; one slot per device ordinal
+  const int dev = current_device();
+  if (dev >= 0 && dev < kMaxDevices) {
+    const int v = cached[dev].load(std::memory_order_relaxed);
+    if (v > 0) return v;
+  }
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
     (void)cudaGetLastError();
     return FKV_NUM_SMS_FALLBACK;
   }
-  cached.store(sms, std::memory_order_relaxed);
+  if (dev >= 0 && dev < kMaxDevices) cached[dev].store(sms, std::memory_order_relaxed);
   return sms;
+}
+
+int ensure_dyn_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::vector<std::pair<int, const void*>> done;   // (device, kernel) pairs already opted in
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lock(mu);
+  for (const auto& e : done)
+    if (e.first == dev && e.second == kernel) return FKV_OK;
+  FKV_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done.emplace_back(dev, kernel);
+  return FKV_OK;
+}
+
+// workspaces that went through fkv_workspace_init in this process: (device, base, bytes)
+struct WsRange { int dev; uintptr_t base; size_t bytes; };
+static std::mutex g_ws_mu;
+static std::vector<WsRange> g_ws;
+
+static void register_workspace(void* ws, size_t bytes) {
+  const int dev = current_device();
+  const uintptr_t b = reinterpret_cast<uintptr_t>(ws);
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  // a new buffer replaces every older registration it overlaps (the allocator handed the range out again)
+  for (size_t i = 0; i < g_ws.size();) {
+    const WsRange& r = g_ws[i];
+    if (r.dev == dev && b < r.base + r.bytes && r.base < b + bytes) { g_ws[i] = g_ws.back(); g_ws.pop_back(); }
+    else ++i;
+  }
+  g_ws.push_back({dev, b, bytes});
+}
+
+bool workspace_registered(const void* ws, size_t bytes) {
+  const int dev = current_device();
+  const uintptr_t b = reinterpret_cast<uintptr_t>(ws);
+  std::lock_guard<std::mutex> lock(g_ws_mu);
+  for (const WsRange& r : g_ws)
+    if (r.dev == dev && b >= r.base && b + bytes <= r.base + r.bytes) return true;
+  return false;
 }
 
 namespace {
@@ -47,7 +99,7 @@ int validate_score(const fkv_score_params& p) {
   if (p.D != 64 && p.D != 128) return FKV_EHEADDIM;
   if (p.B < 1 || p.Hq < 1 || p.Hkv < 1 || p.L < 1 || p.Hq % p.Hkv) return FKV_EINVAL;
   const int G = p.Hq / p.Hkv;
-  if (G != 1 && G != 2 && G != 4 && G != 8) return FKV_EINVAL;
+  if (G > 64) return FKV_EINVAL;                       // any group size: the tensor path splits it into sub-groups of 1/2/4 heads
   if (p.kernel_size < 1 || p.kernel_size > 63 || (p.kernel_size & 1) == 0) return FKV_EPOOL;
   if (p.mode != FKV_MODE_GEMFILTER) {
     if (p.pooling != FKV_POOL_AVG && p.pooling != FKV_POOL_MAX) return FKV_EPOOL;
@@ -64,6 +116,9 @@ int validate_score(const fkv_score_params& p) {
   if (p.workspace == nullptr ||
       p.workspace_bytes < score_workspace_bytes(p.mode, p.B, p.Hq, p.Hkv, p.L, p.window_size))
     return FKV_EWORKSPACE;
+  // the header (launch epoch, departure counter) is persistent state: refuse a buffer that never went through
+  // fkv_workspace_init instead of computing on a garbage epoch (no device-side trap, nothing is launched)
+  if (!workspace_registered(p.workspace, FKV_WORKSPACE_HEADER_BYTES)) return FKV_EWORKSPACE;
   return FKV_OK;
 }
 
@@ -113,22 +168,33 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
   const int k_head = capacity > window_size ? capacity - window_size : 1;
   b += topk_workspace_bytes(B * Hsel, L, k_head);
   if (tsp_k > 0) b += topk_workspace_bytes(B, L, tsp_k);
-  return b + 4096;
+  return b + 4096;                                     // score_workspace_bytes already includes the header
 }
 
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
-  if (!workspace || workspace_bytes < 256) return FKV_EWORKSPACE;
+  if (!workspace || workspace_bytes < FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
   FKV_CUDA_TRY(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)stream));
+  register_workspace(workspace, workspace_bytes);
   // header word 4 = "initialised" mark; the scoring kernel traps on a workspace that never went through here
   static const uint32_t magic = kWorkspaceMagic;
   FKV_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(workspace) + 16, &magic, sizeof(magic), cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return FKV_OK;
 }
 
-size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k) { return topk_workspace_bytes(rows, n, k); }
+size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k) {
+  return FKV_WORKSPACE_HEADER_BYTES + topk_workspace_bytes(rows, n, k);
+}
 
 size_t fkv_decode_workspace_bytes(int32_t B, int32_t Hq, int32_t D, int32_t max_seq_len) {
-  return decode_workspace_bytes(B, Hq, D, max_seq_len);
+  return FKV_WORKSPACE_HEADER_BYTES + decode_workspace_bytes(B, Hq, D, max_seq_len);
+}
+
+int fkv_workspace_status(const void* workspace, void* stream) {
+  if (!workspace) return FKV_EWORKSPACE;
+  uint32_t hdr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  FKV_CUDA_TRY(cudaMemcpyAsync(hdr, workspace, sizeof(hdr), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  FKV_CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  return (hdr[4] == kWorkspaceMagic && hdr[5] == 0u) ? FKV_OK : FKV_EWORKSPACE;
 }
 
 const char* fkv_score_impl_name(const fkv_score_params* p) {
@@ -149,7 +215,13 @@ int fkv_topk(const fkv_topk_params* p, void* stream) {
   if (p->rows < 1 || p->n < 1 || !p->src || !p->out || p->tail < 0) return FKV_EINVAL;
   if (p->k < 1 || p->k > p->n) return FKV_ETOPK;
   if (p->order != FKV_ORDER_VALUE_DESC && p->order != FKV_ORDER_INDEX_ASC) return FKV_EMODE;
-  return launch_topk(*p, (cudaStream_t)stream);
+  fkv_topk_params q = *p;                              // scratch starts past the scoring header
+  if (q.workspace) {
+    if (q.workspace_bytes < FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
+    q.workspace = static_cast<char*>(q.workspace) + FKV_WORKSPACE_HEADER_BYTES;
+    q.workspace_bytes -= FKV_WORKSPACE_HEADER_BYTES;
+  }
+  return launch_topk(q, (cudaStream_t)stream);
 }
 
 int fkv_gather_kv(const fkv_gather_kv_params* p, void* stream) {
@@ -186,9 +258,15 @@ int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream) {
   const int es = dtype_size(p->dtype);
   int rc;
   if ((rc = check_view(p->k_cache, es)) || (rc = check_view(p->v_cache, es))) return rc;
-  if ((p->q_stride_b * es) % 8 || (p->q_stride_h * es) % 8 || (p->out_stride_b * es) % 8 || (p->out_stride_h * es) % 8)
+  if ((p->q_stride_b * es) % 16 || (p->q_stride_h * es) % 16 || (p->out_stride_b * es) % 16 || (p->out_stride_h * es) % 16)
     return FKV_EALIGN;
-  return launch_decode_attn(*p, (cudaStream_t)stream);
+  if (!aligned16(p->q) || !aligned16(p->out)) return FKV_EALIGN;
+  if (p->seq_len_dev && p->max_seq_len < 1) return FKV_EINVAL;      // the device-side length needs its bound
+  fkv_decode_attn_params q = *p;                       // scratch starts past the scoring header
+  if (!q.workspace || q.workspace_bytes < FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
+  q.workspace = static_cast<char*>(q.workspace) + FKV_WORKSPACE_HEADER_BYTES;
+  q.workspace_bytes -= FKV_WORKSPACE_HEADER_BYTES;
+  return launch_decode_attn(q, (cudaStream_t)stream);
 }
 
 int fkv_cache_append(const fkv_cache_append_params* p, void* stream) {

@@ -66,7 +66,14 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif
-int num_sms();   // cached cudaDevAttrMultiProcessorCount of the current device (abi.cu)
+int num_sms();   // cudaDevAttrMultiProcessorCount of the CURRENT device, cached per device (abi.cu)
+// Opt a kernel in to `bytes` of dynamic shared memory once per (device, kernel): function attributes are per
+// device, and several host threads may launch concurrently (abi.cu; mutex-guarded, a no-op after the first call).
+int ensure_dyn_smem(const void* kernel, int bytes);
+template <typename K>
+inline int ensure_dyn_smem(K* kernel, int bytes) { return ensure_dyn_smem(reinterpret_cast<const void*>(kernel), bytes); }
+// true iff `ws` lies inside a buffer that went through fkv_workspace_init in this process (abi.cu)
+bool workspace_registered(const void* ws, size_t bytes);
 
 // ---- element loads -> fp32 -----------------------------------------------------------------
 template <typename T> struct Elem;

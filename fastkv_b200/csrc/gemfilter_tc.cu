@@ -225,11 +225,7 @@ int launch_gemfilter_tensor(const fkv_score_params& p, cudaStream_t s) {
   int rc;
   if ((rc = make_map(&mk, p.k, p.dtype, p.B, p.Hkv, p.L, p.D, kTile, &a.kpos_l, &a.kpos_h, &a.kpos_b)) != FKV_OK) return rc;
   if ((rc = make_map(&mq, p.q, p.dtype, p.B, p.Hq, p.L, p.D, 1, &a.qpos_l, &a.qpos_h, &a.qpos_b)) != FKV_OK) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    FKV_CUDA_TRY(cudaFuncSetAttribute(gemfilter_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  { const int rc_attr = ensure_dyn_smem(gemfilter_tc_kernel, 227 * 1024); if (rc_attr != FKV_OK) return rc_attr; }
   FKV_CUDA_TRY(launch_pdl(gemfilter_tc_kernel, dim3(pl.grid), dim3(kGfThreads), pl.smem, s, mk, mq, a));
   count_launch();
   return FKV_OK;

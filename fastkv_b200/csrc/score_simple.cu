@@ -256,13 +256,12 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
   const int n_tiles = ceil_div(p.L, kTileKeys);
   a.n_tiles = n_tiles;
   const size_t smem = (size_t)(kTileKeys * (p.D + 4) + kRowChunk * p.D + kRowChunk * (kTileKeys + 1)) * sizeof(float);
-  static bool attr_set = false;                      // once per process (and never inside a graph capture)
-  if (!attr_set) {
+  {                                                  // once per (device, kernel)
     const int smem_max = (int)((kTileKeys * (128 + 4) + kRowChunk * 128 + kRowChunk * (kTileKeys + 1)) * sizeof(float));
-    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kVotes>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tile_kernel<T, kRaw>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    attr_set = true;
+    int rc_attr;
+    if ((rc_attr = ensure_dyn_smem(score_tile_kernel<T, kStats>, smem_max)) != FKV_OK) return rc_attr;
+    if ((rc_attr = ensure_dyn_smem(score_tile_kernel<T, kVotes>, smem_max)) != FKV_OK) return rc_attr;
+    if ((rc_attr = ensure_dyn_smem(score_tile_kernel<T, kRaw>, smem_max)) != FKV_OK) return rc_attr;
   }
   char* ws = reinterpret_cast<char*>(p.workspace) + 256;   // the first 256 bytes hold the tensor path's barrier counters
 

@@ -226,12 +226,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     float mn[N], z[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
-    // a workspace that never went through fkv_workspace_init has a garbage departure counter / epoch and would
-    // make stale records look valid: fail loudly instead of computing on them
-    if (et == 0 && blockIdx.x == 0 && __ldcg(a.sync_counter + 4) != kWorkspaceMagic) {
-      printf("fastkv_b200: fkv_score got a workspace that was not passed through fkv_workspace_init\n");
-      __trap();
-    }
+    // The host side refuses workspaces that never went through fkv_workspace_init (FKV_EWORKSPACE).  Should the
+    // header be overwritten afterwards, never abort the context across the ABI: flag it in the header's error word
+    // (read back by fkv_workspace_status) and carry on; the launch stays self-consistent (all CTAs read one epoch).
+    if (et == 0 && blockIdx.x == 0 && __ldcg(a.sync_counter + 4) != kWorkspaceMagic) a.sync_counter[5] = 1u;
     // launch epoch (bumped by the last CTA of every launch) -> the two record tags of this launch
     const unsigned long long epoch = __ldcg(reinterpret_cast<const unsigned long long*>(a.sync_counter + 2)) + 1ull;
     const unsigned int tag_m = 0x7fc00000u | (unsigned)(epoch & 0x3fffffu);
@@ -510,7 +508,7 @@ Plan make_plan(const fkv_score_params& p) {
   // At most 32 logit rows per MMA tile (running max + sum + logits = 96 live registers per epilogue thread):
   // wider groups (W=16/32 at G=4, G=8 models) run as several launches over head sub-groups, each reading K once.
   int Gk = Gm;
-  while (Gk > 1 && (Gk * pl.W > 32 || Gm % Gk)) --Gk;
+  while (Gk > 1 && (Gk * pl.W > 32 || Gm % Gk || (Gk != 2 && Gk != 4))) --Gk;   // instances exist for 1, 2 and 4 heads
   if (Gk * pl.W > 32) return pl;
   pl.G = Gk; pl.Gm = Gm; pl.N = pl.G * pl.W;
   if (p.mode == FKV_MODE_SNAPKV) {
@@ -565,11 +563,7 @@ Plan make_plan(const fkv_score_params& p) {
 
 template <int W, int G, bool kDef>
 int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, int grid, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FKV_CUDA_TRY(cudaFuncSetAttribute(score_tc_kernel<W, G, kDef>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  { const int rc_attr = ensure_dyn_smem(score_tc_kernel<W, G, kDef>, 227 * 1024); if (rc_attr != FKV_OK) return rc_attr; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kTcThreads);

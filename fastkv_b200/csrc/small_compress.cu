@@ -496,11 +496,7 @@ SfPlan make_sf_plan(const fkv_compress_params& cp) {
 
 template <int W, int G>
 int launch_sf_inst(const CUtensorMap& mk, const CUtensorMap& mq, const SfArgs& a, int n_ctas, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    FKV_CUDA_TRY(cudaFuncSetAttribute(small_compress_kernel<W, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  { const int rc_attr = ensure_dyn_smem(small_compress_kernel<W, G>, 227 * 1024); if (rc_attr != FKV_OK) return rc_attr; }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(n_ctas);
   cfg.blockDim = dim3(kSfThreads);

@@ -185,8 +185,47 @@ EncodeTiledFn encode_fn() {
 
 // [B,H,L,D] view -> 4-D tensor map (dim0 = D, the other three sorted by stride) with a
 // (64 x box_rows x 1 x 1) box on (D, L); reports the coordinate slot of l / h / b.
+// Encoded maps are cached per translation unit, keyed by everything that enters the encoding (pointer, dtype, shape,
+// strides, box): a prefill calls the same layer buffers again and again, and cuTensorMapEncodeTiled costs ~1 us of host
+// time per map.  Mutex-guarded (the C ABI is re-entrant), 64 entries, round-robin replacement.
+struct MapKey {
+  const void* ptr; int64_t sb, sh, sl; int dtype, B, H, L, D, box_rows;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && sb == o.sb && sh == o.sh && sl == o.sl && dtype == o.dtype && B == o.B && H == o.H && L == o.L &&
+           D == o.D && box_rows == o.box_rows;
+  }
+};
+struct MapEntry { MapKey key; CUtensorMap map; int pos_l, pos_h, pos_b; bool valid; };
+
+int make_map_uncached(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int L, int D, int box_rows, int* pos_l,
+                      int* pos_h, int* pos_b);
+
 int make_map(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int L, int D, int box_rows, int* pos_l,
              int* pos_h, int* pos_b) {
+  constexpr int kEntries = 64;
+  static std::mutex mu;
+  static MapEntry cache[kEntries];
+  static int next = 0;
+  const MapKey key{v.ptr, v.stride_b, v.stride_h, v.stride_l, dtype, B, H, L, D, box_rows};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < kEntries; ++i)
+      if (cache[i].valid && cache[i].key == key) {
+        *map = cache[i].map; *pos_l = cache[i].pos_l; *pos_h = cache[i].pos_h; *pos_b = cache[i].pos_b;
+        return FKV_OK;
+      }
+  }
+  const int rc = make_map_uncached(map, v, dtype, B, H, L, D, box_rows, pos_l, pos_h, pos_b);
+  if (rc != FKV_OK) return rc;
+  std::lock_guard<std::mutex> lock(mu);
+  MapEntry& e = cache[next];
+  next = (next + 1) % kEntries;
+  e.key = key; e.map = *map; e.pos_l = *pos_l; e.pos_h = *pos_h; e.pos_b = *pos_b; e.valid = true;
+  return FKV_OK;
+}
+
+int make_map_uncached(CUtensorMap* map, const fkv_view4& v, int dtype, int B, int H, int L, int D, int box_rows, int* pos_l,
+                      int* pos_h, int* pos_b) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return (int)cudaErrorNotSupported;
   struct Dim { uint64_t size, stride; int box, id; } d[3] = {

@@ -750,13 +750,10 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
       if (fused) *fused = true;
     }
     a.write_dense = (a.nsum > 1);                   // the fallback inside the kernel needs the dense row
-    static bool attr_set = false;
-    if (!attr_set) {
-      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(ClusterSmem)));
-      FKV_CUDA_TRY(cudaFuncSetAttribute(topk_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)sizeof(ClusterSmem)));
-      attr_set = true;
+    {
+      int rc_attr;
+      if ((rc_attr = ensure_dyn_smem(topk_cluster_kernel<true>, (int)sizeof(ClusterSmem))) != FKV_OK) return rc_attr;
+      if ((rc_attr = ensure_dyn_smem(topk_cluster_kernel<false>, (int)sizeof(ClusterSmem))) != FKV_OK) return rc_attr;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(p.rows * Cp);
@@ -799,11 +796,10 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
       a.sort_ws = reinterpret_cast<unsigned long long*>(ws + off);
     }
   }
-  static bool attr_set_row = false;
-  if (!attr_set_row) {
+  {
     const int smem_max = (int)((kMaxBins + kWarps + 4) * sizeof(uint32_t) + (size_t)kSmemSortMax * sizeof(unsigned long long));
-    FKV_CUDA_TRY(cudaFuncSetAttribute(topk_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    attr_set_row = true;
+    const int rc_attr = ensure_dyn_smem(topk_row_kernel, smem_max);
+    if (rc_attr != FKV_OK) return rc_attr;
   }
   topk_row_kernel<<<p.rows, kThreads, smem, s>>>(a);
   FKV_LAUNCH_CHECK();

@@ -33,6 +33,14 @@ def _score_params(mode, q, k, window_size, kernel_size, pooling, score, h0, h1, 
     return p
 
 
+def _check_kv_pair(k: torch.Tensor, v: torch.Tensor):
+    """The kernels copy V with K's dtype and geometry: refuse a mismatched pair instead of mis-reading V."""
+    if v.dtype != k.dtype:
+        raise ValueError(f"fastkv_b200: key/value dtype mismatch ({k.dtype} vs {v.dtype})")
+    if tuple(v.shape) != tuple(k.shape):
+        raise ValueError(f"fastkv_b200: key/value shape mismatch ({tuple(k.shape)} vs {tuple(v.shape)})")
+
+
 def selection_heads(mode: int, Hq: int, Hkv: int) -> int:
     return Hkv if mode == L.MODE_FASTKV else (Hq if mode == L.MODE_SNAPKV else 1)
 
@@ -101,6 +109,7 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, *, window_siz
     L.require_cuda_or_pinned(k, v)
     lib = L.load()
     B, _, Lk, D = k.shape
+    _check_kv_pair(k, v)
     Hsel, n_sel = idx.shape[1], idx.shape[2]
     h0, h1 = head_range if head_range is not None else (0, Hsel)
     if idx.dtype != torch.int64 or idx.stride(2) != 1:
@@ -118,7 +127,7 @@ def gather_kv(k: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, *, window_siz
     p.k, p.v = L.view4(k), L.view4(v)
     p.idx, p.idx_stride_b, p.idx_stride_h = idx.data_ptr(), idx.stride(0), idx.stride(1)
     p.k_out, p.v_out = L.view4(k_out), L.view4(v_out)
-    L.check(lib.fkv_gather_kv(C.byref(p), L.stream_ptr(k.device)))
+    L.check(lib.fkv_gather_kv(C.byref(p), L.stream_ptr(idx.device)))     # idx is always on the GPU; K/V may be pinned host
     return k_out, v_out
 
 
@@ -206,6 +215,7 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
     lib = L.load()
     B, Hq, Lq, D = q.shape
     Hkv = k.shape[1]
+    _check_kv_pair(k, v)
     hs = selection_heads(mode, Hq, Hkv)
     h0, h1 = head_range if head_range is not None else (0, hs)
     Hsel = h1 - h0

@@ -30,6 +30,14 @@ from .cluster import FastKVCluster, SnapKVCluster
 _ORIGINALS = {}
 
 
+def _repeat_kv(x, n_rep):
+    """[B,Hkv,S,D] -> [B,Hkv*n_rep,S,D] (query head hq reads kv head hq // n_rep), baselines/snapkv/llama_model.py:385."""
+    if n_rep == 1:
+        return x
+    b, h, s, d = x.shape
+    return x[:, :, None, :, :].expand(b, h, n_rep, s, d).reshape(b, h * n_rep, s, d)
+
+
 # ---------------------------------------------------------------------------------------------
 # knob plumbing (same attribute / argument names as the reference)
 # ---------------------------------------------------------------------------------------------
@@ -117,6 +125,32 @@ def set_model(model, args):
             layer.self_attn.kv_cluster.kernel_size = kernel_size[i]
 
 
+def _prefill_mask(config, q_len, like, use_sliding_window):
+    """(attention_mask, extra kwargs) for the attention interface of ``config._attn_implementation``.
+
+    The reference always runs flash-attn with ``causal=True`` (+ ``sliding_window`` on Mistral,
+    baselines/fastkv/mistral_model.py:143-153).  ``sdpa`` / ``flash_attention_*`` take the causal flag; ``eager``
+    (and any interface that ignores ``is_causal``) gets an explicit additive mask, otherwise its prefill would be
+    bidirectional.  A sliding window shorter than the prompt needs the band mask as well (sdpa) or the flash
+    kernels' window argument."""
+    impl = getattr(config, "_attn_implementation", None) or "eager"
+    window = getattr(config, "sliding_window", None) if use_sliding_window else None
+    if q_len == 1:
+        return None, {"is_causal": False}
+    banded = window is not None and q_len > window
+    if impl.startswith("flash_attention") or (impl == "sdpa" and not banded):
+        return None, {}                                # causal flag (+ sliding_window kwarg for the flash kernels)
+    if impl not in ("sdpa", "eager"):
+        raise NotImplementedError(f"fastkv_b200: attention implementation {impl!r} is not supported on the FastKV path "
+                                  "(use sdpa, flash_attention_2 or eager)")
+    i = torch.arange(q_len, device=like.device)
+    keep = i[None, :] <= i[:, None]
+    if banded:
+        keep &= (i[:, None] - i[None, :]) < window
+    mask = torch.zeros((q_len, q_len), dtype=like.dtype, device=like.device).masked_fill_(~keep, torch.finfo(like.dtype).min)
+    return mask[None, None], {"is_causal": False}
+
+
 # ---------------------------------------------------------------------------------------------
 # patched forwards (shared by Llama and Mistral; `mod` is the transformers modeling module)
 # ---------------------------------------------------------------------------------------------
@@ -136,6 +170,7 @@ def _make_forwards(mod, method, sliding_window_attr=False):
         cos, sin = position_embeddings
         query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
 
+        self.tsp_idx = None                            # never let a previous call's selection leak into this one
         decode_native = False
         if past_key_values is not None:
             if q_len > 1:
@@ -157,10 +192,13 @@ def _make_forwards(mod, method, sliding_window_attr=False):
                     self.tsp_idx = None
                 past_key_values.update(k_c, v_c, self.layer_idx)
             else:
-                self.tsp_idx = None
+                if method == "snapkv" and key_states.shape[1] != query_states.shape[1]:
+                    # the SnapKV cache holds one head per QUERY head (snapkv/llama_model.py:385-386 repeat_kv's before
+                    # the cache update in both phases): expand the new row the same way before appending it
+                    key_states = _repeat_kv(key_states, self.num_key_value_groups)
+                    value_states = _repeat_kv(value_states, self.num_key_value_groups)
                 native_ok = (isinstance(past_key_values, CompactKVCache) and key_states.is_cuda
-                             and key_states.shape[1] * self.num_key_value_groups == query_states.shape[1]
-                             and self.head_dim in (64, 128))
+                             and query_states.shape[1] % key_states.shape[1] == 0 and self.head_dim in (64, 128))
                 if native_ok and past_key_values.device_lengths:
                     # CUDA-graph friendly step: the row index and the attended length live on the device
                     kbuf, vbuf, _, ndev = past_key_values.buffers(self.layer_idx)
@@ -177,8 +215,6 @@ def _make_forwards(mod, method, sliding_window_attr=False):
             attn_output = out.reshape(input_shape[0], 1, -1)
             attn_weights = None
         else:
-            if method == "snapkv" and key_states.shape[1] != query_states.shape[1] and q_len == 1:
-                pass                                  # GQA handled by the attention interface
             attention_interface = ALL_ATTENTION_FUNCTIONS.get_interface(self.config._attn_implementation, eager_attention_forward)
             extra = {}
             if sliding_window_attr:
@@ -228,14 +264,16 @@ def _make_forwards(mod, method, sliding_window_attr=False):
             past_seen = past_key_values.get_seq_length() if past_key_values is not None else 0
             position_ids = (torch.arange(inputs_embeds.shape[1], device=inputs_embeds.device) + past_seen).unsqueeze(0)
         q_len = inputs_embeds.shape[1]
+        if isinstance(past_key_values, CompactKVCache):
+            past_key_values.note_tokens(q_len)         # true (un-compacted) token count, read by the generate() path
         if attention_mask is not None and attention_mask.dim() == 2 and not bool(attention_mask.all()):
             # the reference's padded-batch path is broken (llama_model.py:57,77)
             raise NotImplementedError("padded batches are not supported on the FastKV path")
-        # un-padded prompts: pure causal attention (prefill) / everything visible (decode)
-        causal_mask = None
+        # un-padded prompts: causal attention (prefill, optionally inside Mistral's sliding window) / everything
+        # visible (decode over a compact cache that is always shorter than the window)
         hidden_states = inputs_embeds
         position_embeddings = self.rotary_emb(hidden_states, position_ids=position_ids)
-        is_causal_kw = {} if q_len > 1 else {"is_causal": False}
+        causal_mask, is_causal_kw = _prefill_mask(self.config, q_len, hidden_states, sliding_window_attr)
         for decoder_layer in self.layers[: self.config.num_hidden_layers]:
             hidden_states = decoder_layer(
                 hidden_states, attention_mask=causal_mask, position_embeddings=position_embeddings,
@@ -244,6 +282,9 @@ def _make_forwards(mod, method, sliding_window_attr=False):
             if new_position_ids is not None:          # [FastKV] later layers run on the TSP-selected tokens only
                 position_ids = new_position_ids
                 position_embeddings = self.rotary_emb(hidden_states, position_ids=position_ids)
+                # the kept tokens stay in ascending order: still causal (and banded by INDEX, as the reference's
+                # flash-attn call is) over the shorter sequence
+                causal_mask, is_causal_kw = _prefill_mask(self.config, hidden_states.shape[1], hidden_states, sliding_window_attr)
         hidden_states = self.norm(hidden_states)
         hidden_states = hidden_states[:, -1:, :]      # [FastKV] only the last token feeds lm_head
         return BaseModelOutputWithPast(last_hidden_state=hidden_states, past_key_values=past_key_values)
@@ -284,17 +325,91 @@ def _make_gemfilter_attn_forward(mod, sliding_window_attr=False):
     return attn_forward
 
 
+# ---------------------------------------------------------------------------------------------
+# generate() path: decode positions continue from the TRUE prompt length (monkeypatch.py:249-389)
+# ---------------------------------------------------------------------------------------------
+def _prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
+                                   cache_position=None, position_ids=None, use_cache=True, **kwargs):
+    """``prepare_inputs_for_generation_llama`` / ``_mistral`` of the reference (baselines/monkeypatch.py:249-330,
+    :333-389), re-hosted on the installed transformers.
+
+    The point of the override (:280-288): with a COMPACTED cache the number of cached rows says nothing about
+    where the next token sits, so position ids come from the attention mask (``cumsum - 1``, last
+    ``input_ids.shape[1]`` entries) — i.e. they continue from the true prompt length — or, when no mask is
+    given, from the cache's own count of tokens seen (``CompactKVCache.true_length``)."""
+    has_past = past_key_values is not None and past_key_values.get_seq_length() > 0
+    true_len = getattr(past_key_values, "true_length", None) if has_past else None
+    if has_past:
+        if inputs_embeds is not None and cache_position is not None:                      # Exception 1 (:273-274)
+            input_ids = input_ids[:, -cache_position.shape[0]:]
+        elif cache_position is not None and input_ids.shape[1] != cache_position.shape[0]:  # default case (:275-276)
+            input_ids = input_ids[:, cache_position]
+        elif cache_position is None and input_ids.shape[1] > 1:
+            # transformers >= 5 passes no cache_position but the number of unprocessed tokens
+            nxt = kwargs.get("next_sequence_length")
+            if nxt is not None:
+                input_ids = input_ids[:, -int(nxt):]
+            else:
+                seen = true_len if true_len else (attention_mask.shape[1] - 1 if attention_mask is not None else input_ids.shape[1] - 1)
+                input_ids = input_ids[:, seen:]
+    if attention_mask is not None and position_ids is None:                               # :278-288
+        position_ids = attention_mask.long().cumsum(-1) - 1
+        position_ids.masked_fill_(attention_mask == 0, 1)
+        if has_past:
+            position_ids = position_ids[:, -input_ids.shape[1]:]
+        position_ids = position_ids.clone(memory_format=torch.contiguous_format)
+    elif position_ids is None and has_past and true_len:
+        n = input_ids.shape[1]
+        position_ids = torch.arange(true_len, true_len + n, device=input_ids.device).unsqueeze(0).expand(input_ids.shape[0], -1).contiguous()
+    elif position_ids is not None and has_past and position_ids.shape[1] != input_ids.shape[1]:
+        # full-length position ids built by generate() from the mask: keep the unprocessed tokens' (true) positions
+        position_ids = position_ids[:, -input_ids.shape[1]:].clone(memory_format=torch.contiguous_format)
+    if inputs_embeds is not None and not has_past:                                        # :291-295
+        model_inputs = {"inputs_embeds": inputs_embeds, "input_ids": None}
+    else:
+        model_inputs = {"input_ids": input_ids.clone(memory_format=torch.contiguous_format), "inputs_embeds": None}
+    model_inputs.update({"position_ids": position_ids, "cache_position": cache_position, "past_key_values": past_key_values,
+                         "use_cache": use_cache, "attention_mask": attention_mask})
+    for k, v in kwargs.items():                        # e.g. logits_to_keep: pass through untouched
+        if k not in ("next_sequence_length", "is_first_iteration"):
+            model_inputs.setdefault(k, v)
+    return model_inputs
+
+
+def prepare_inputs_for_generation_llama(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
+                                        cache_position=None, position_ids=None, use_cache=True, **kwargs):
+    """baselines/monkeypatch.py:249-330."""
+    return _prepare_inputs_for_generation(self, input_ids, past_key_values, attention_mask, inputs_embeds, cache_position,
+                                          position_ids, use_cache, **kwargs)
+
+
+def prepare_inputs_for_generation_mistral(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None,
+                                          cache_position=None, position_ids=None, use_cache=True, **kwargs):
+    """baselines/monkeypatch.py:333-389 (the sliding-window crop of the attention mask there, :352-360, only acts on
+    caches longer than the window, which a compact cache never is)."""
+    return _prepare_inputs_for_generation(self, input_ids, past_key_values, attention_mask, inputs_embeds, cache_position,
+                                          position_ids, use_cache, **kwargs)
+
+
 def _patch(mod, prefix, method, sliding):
     attn_cls = getattr(mod, prefix + "Attention")
     layer_cls = getattr(mod, prefix + "DecoderLayer")
     model_cls = getattr(mod, prefix + "Model")
+    lm_cls = getattr(mod, prefix + "ForCausalLM")
     key = prefix
     if key not in _ORIGINALS:
-        _ORIGINALS[key] = (attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__)
-    o_attn, o_layer, o_model, o_init = _ORIGINALS[key]
+        _ORIGINALS[key] = (attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__,
+                           lm_cls.prepare_inputs_for_generation)
+    o_attn, o_layer, o_model, o_init, o_prep = _ORIGINALS[key]
     if method == "fullkv":
         attn_cls.forward, layer_cls.forward, model_cls.forward, attn_cls.__init__ = o_attn, o_layer, o_model, o_init
+        lm_cls.prepare_inputs_for_generation = o_prep
         return
+    if method not in ("fastkv", "snapkv", "gemfilter"):
+        raise NotImplementedError(f"No method found for {method}: only fastkv / snapkv / gemfilter / fullkv are on the hot path")
+    # every method but fullkv decodes from the true prompt length (monkeypatch.py:55-56, :101-102)
+    lm_cls.prepare_inputs_for_generation = (prepare_inputs_for_generation_mistral if prefix == "Mistral"
+                                            else prepare_inputs_for_generation_llama)
     if method == "gemfilter":
         # selection-mode baseline: only the attention forward differs from stock (gemfilter/llama_model.py)
         gf_forward = _make_gemfilter_attn_forward(mod, sliding_window_attr=sliding)
@@ -312,8 +427,6 @@ def _patch(mod, prefix, method, sliding):
         attn_cls.__init__, attn_cls.forward = gemfilter_init, gf_forward
         layer_cls.forward, model_cls.forward = o_layer, o_model
         return
-    if method not in ("fastkv", "snapkv"):
-        raise NotImplementedError(f"No method found for {method}: only fastkv / snapkv / gemfilter / fullkv are on the hot path")
     attn_f, layer_f, model_f = _make_forwards(mod, method, sliding_window_attr=sliding)
 
     def patched_init(self, *args, **kwargs):
@@ -364,7 +477,8 @@ class GraphedDecode:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._step()
-        # the capture itself did not execute: nothing to undo
+        # the capture itself did not execute: nothing to undo on the device; the host-side token count did advance
+        cache.true_length -= 1
         # the graph bakes in the scratch pointer of the decode kernels: keep that buffer alive even if a
         # later, larger call replaces it in the per-stream table
         from . import _lib as _L
@@ -379,11 +493,18 @@ class GraphedDecode:
     @torch.no_grad()
     def generate(self, n):
         """n more tokens (after the warm-up ones); returns [B, warmup + n] token ids."""
+        self.cache.sync_lengths()
+        room = min(k.shape[2] - s for k, s in zip(self.cache.k, self.cache.seq_lens) if k is not None)
+        if n > room:
+            # the replayed step appends through device-side lengths: the host check of CompactKVCache.update is not on
+            # that path, so refuse here instead of dropping rows silently
+            raise RuntimeError(f"CompactKVCache has room for {room} more tokens, {n} requested: raise max_new_tokens")
         toks = list(self.eager_tokens)
         for _ in range(n):
             self.graph.replay()
             toks.append(self.tok.clone())
         self.cache.sync_lengths()
+        self.cache.true_length += n
         return torch.cat(toks, dim=1)
 
 

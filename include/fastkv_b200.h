@@ -21,7 +21,15 @@
 extern "C" {
 #endif
 
-#define FKV_ABI_VERSION 3
+#define FKV_ABI_VERSION 4
+
+/* Every `workspace` argument below is one kind of buffer: device memory, 256-byte aligned, passed ONCE through
+ * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state of the scoring kernel (launch
+ * epoch, departure counter, error word); every entry point that uses a workspace as scratch (fkv_topk,
+ * fkv_decode_attn, the top-k stages of fkv_compress) starts PAST that header by itself, so one buffer can be
+ * shared by all calls issued on a stream and no caller ever has to offset a pointer.  The *_workspace_bytes
+ * queries include the header. */
+#define FKV_WORKSPACE_HEADER_BYTES 256
 
 /* ---- enums ------------------------------------------------------------------------------- */
 enum { FKV_BF16 = 0, FKV_F16 = 1, FKV_F32 = 2 };                 /* element type of Q/K/V/hidden   */
@@ -153,7 +161,8 @@ int fkv_gather_rows(const fkv_gather_rows_params* p, void* stream);
  * mistral_model.py:143-153): out[b,hq,:] = softmax(q[b,hq,:] . K[b,hq/G,0:S,:]^T * scale) V.
  * q/out are [B,Hq,D] with stride_b / stride_h (elements); caches are [B,Hkv,S_max,D] views.
  * S is `seq_len`, or *seq_len_dev (int32 on device, read by the kernel) when that is non-NULL so
- * a captured CUDA graph can be replayed while the cache grows.
+ * a captured CUDA graph can be replayed while the cache grows; either way S is clamped to
+ * max_seq_len (> 0), the number of rows the cache views really have.
  */
 typedef struct fkv_decode_attn_params {
   uint32_t struct_size;
@@ -172,7 +181,8 @@ int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream);
 /*
  * Appends one new K/V row per (b, kv head) at row *seq_len_dev (or seq_len) of the cache and,
  * if bump != 0, increments *seq_len_dev afterwards (replaces DynamicCache.update's torch.cat at
- * baselines/fastkv/llama_model.py:144).  k_new/v_new are [B,Hkv,1,D] views.
+ * baselines/fastkv/llama_model.py:144).  k_new/v_new are [B,Hkv,1,D] views.  A full cache
+ * (row index >= max_seq_len) drops the row AND leaves *seq_len_dev unchanged.
  */
 typedef struct fkv_cache_append_params {
   uint32_t struct_size;
@@ -210,12 +220,15 @@ int fkv_compress(const fkv_compress_params* p, void* stream);
 /* ---- queries ----------------------------------------------------------------------------- */
 /* Bytes of scratch fkv_score / fkv_topk / fkv_compress need for these sizes (upper bound).     */
 /* A workspace must be passed through fkv_workspace_init ONCE after allocation: it zeroes the buffer,
- * i.e. the 256-byte header (departure counter + launch epoch of the scoring kernel) and the region
- * where CTAs exchange epoch-tagged partial softmax statistics.  Calls keep the header consistent.
- * (fkv_score traps with a device-side message when the workspace never went through fkv_workspace_init.)
- * The header is persistent state of fkv_score / fkv_compress: do not pass the same pointer as the
- * scratch of fkv_topk / fkv_decode_attn (offset it by 256 bytes, or use a separate buffer). */
+ * i.e. the header (departure counter + launch epoch of the scoring kernel) and the region where CTAs
+ * exchange epoch-tagged partial softmax statistics, and registers the address range with the library.
+ * fkv_score / fkv_compress return FKV_EWORKSPACE (nothing is launched, nothing traps) for a buffer
+ * that never went through it.  Calls keep the header consistent. */
 int fkv_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+/* Debugging aid, SYNCHRONISES `stream`: reads the header back and returns FKV_OK, or FKV_EWORKSPACE
+ * when the header is not an initialised one or a kernel flagged it as inconsistent (a kernel never
+ * aborts the context: it flags the header and carries on). */
+int fkv_workspace_status(const void* workspace, void* stream);
 size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int32_t L, int32_t window_size,
                            int32_t capacity, int32_t tsp_k);
 size_t fkv_topk_workspace_bytes(int32_t rows, int32_t n, int32_t k);

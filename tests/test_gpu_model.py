@@ -27,6 +27,18 @@ def _args(**kw):
     return types.SimpleNamespace(**base)
 
 
+def _check_cache_rows(idx, ref_idx, k_got, v_got, k_ref, v_ref, w):
+    """Compact cache == the oracle's at every position where the score-descending orders agree (only near-tie swaps
+    may differ), window rows always."""
+    same = idx == ref_idx
+    assert same.float().mean().item() > 0.97, same.float().mean().item()
+    nsel = idx.shape[-1]
+    assert torch.allclose(k_got[:, :, :nsel][same], k_ref[:, :, :nsel][same], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(v_got[:, :, :nsel][same], v_ref[:, :, :nsel][same], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(k_got[:, :, nsel:], k_ref[:, :, nsel:], atol=2e-4, rtol=1e-4)
+    assert torch.allclose(v_got[:, :, nsel:], v_ref[:, :, nsel:], atol=2e-4, rtol=1e-4)
+
+
 @pytest.fixture
 def patched():
     from fastkv_b200 import patch
@@ -63,12 +75,11 @@ def test_fp32_prefill_matches_glue_oracle(patched):
         k_ref, v_ref, _ = ref_caches[i]
         kbuf, vbuf, n, _ = cache.buffers(i)
         assert n == k_ref.shape[2] == 128
-        idx = gm.model.layers[i].self_attn.kv_cluster.last_aux["idx"].cpu()
-        if torch.equal(idx, traces[i].idx):
-            assert torch.allclose(kbuf[:, :, :n].cpu(), k_ref, atol=2e-4, rtol=1e-4)
-            assert torch.allclose(vbuf[:, :, :n].cpu(), v_ref, atol=2e-4, rtol=1e-4)
-    if torch.equal(tsp.cpu(), ref_caches[1][2]):
-        assert torch.allclose(out.last_hidden_state.cpu(), ref_hidden, atol=2e-3, rtol=1e-3)
+        _check_cache_rows(gm.model.layers[i].self_attn.kv_cluster.last_aux["idx"].cpu(), traces[i].idx, kbuf[:, :, :n].cpu(),
+                          vbuf[:, :, :n].cpu(), k_ref, v_ref, 8)
+    # the propagated token set is the oracle's, so the last hidden state must be too (fp32 model)
+    assert torch.equal(tsp.cpu(), ref_caches[1][2])
+    assert torch.allclose(out.last_hidden_state.cpu(), ref_hidden, atol=2e-3, rtol=1e-3)
     assert out.last_hidden_state.shape == (2, 1, 512)
 
 
@@ -192,3 +203,141 @@ def test_proportional_preset_end_to_end(patched):
     tsp = gm.model.layers[tsp_idx].self_attn.tsp_idx
     assert tsp.shape == (1, t) and gm.model.layers[tsp_idx].self_attn.kv_cluster.tsp_length == t
     assert O.near_tie_set_mismatch(traces[tsp_idx].importance[0], ref_caches[tsp_idx][2][0, :-8], tsp[0, :-8].cpu()) == 0
+
+
+# ---------------------------------------------------------------------------------------------
+# Mistral glue (baselines/fastkv/mistral_model.py:100-107, :217-224, :328-330, :351)
+# ---------------------------------------------------------------------------------------------
+def _mistral(dtype, sliding_window, impl="sdpa", layers=3, seed=0):
+    from transformers import MistralConfig, MistralForCausalLM
+    cfg = MistralConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=layers, num_attention_heads=8,
+                        num_key_value_heads=2, head_dim=64, vocab_size=211, max_position_embeddings=65536,
+                        sliding_window=sliding_window, attn_implementation=impl)
+    torch.manual_seed(seed)
+    return MistralForCausalLM(cfg).eval().to(dtype)
+
+
+@pytest.mark.parametrize("sliding_window,impl", [(32768, "sdpa"), (200, "sdpa"), (200, "eager")])
+def test_mistral_fp32_prefill_matches_glue_oracle(sliding_window, impl):
+    """Mistral twin of the Llama test: Ministral's sliding_window=32768 (a no-op at this length, as at 32k) and a window
+    shorter than the prompt (index-banded causal attention, flash-attn's ``sliding_window`` semantics)."""
+    from transformers.models.mistral.modeling_mistral import apply_rotary_pos_emb
+    from fastkv_b200 import patch
+    ids = torch.randint(0, 211, (2, 600), generator=torch.Generator().manual_seed(13))
+    knobs = [dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=(i == 1), tsp_length=256)
+             for i in range(3)]
+    patch.replace_mistral("fullkv")
+    model = _mistral(torch.float32, sliding_window, impl)
+    ref_hidden, ref_caches, traces = G.fastkv_prefill(model, ids, knobs, apply_rotary_pos_emb, sliding_window=sliding_window)
+    patch.replace_mistral("fastkv")
+    try:
+        gm = _mistral(torch.float32, sliding_window, impl).to(DEV)
+        patch.set_model(gm, _args())
+        for layer in gm.model.layers:
+            layer.self_attn.kv_cluster.keep_aux = True
+        with torch.no_grad():
+            out = gm.model(ids.to(DEV), use_cache=True)
+        torch.cuda.synchronize()
+        cache = out.past_key_values
+        tsp = gm.model.layers[1].self_attn.tsp_idx
+        assert tsp is not None and tsp.shape == (2, 256)
+        assert torch.equal(gm.model.layers[1].new_position_ids.cpu(), tsp.cpu())       # mistral_model.py:220-222
+        for b in range(2):
+            assert O.near_tie_set_mismatch(traces[1].importance[b], ref_caches[1][2][b, :-8], tsp[b, :-8].cpu()) == 0
+        for i in range(3):
+            k_ref, v_ref, _ = ref_caches[i]
+            kbuf, vbuf, n, _ = cache.buffers(i)
+            assert n == k_ref.shape[2] == 128
+            _check_cache_rows(gm.model.layers[i].self_attn.kv_cluster.last_aux["idx"].cpu(), traces[i].idx,
+                              kbuf[:, :, :n].cpu(), vbuf[:, :, :n].cpu(), k_ref, v_ref, 8)
+        assert torch.equal(tsp.cpu(), ref_caches[1][2])
+        assert torch.allclose(out.last_hidden_state.cpu(), ref_hidden, atol=2e-3, rtol=1e-3)
+    finally:
+        patch.replace_mistral("fullkv")
+
+
+def test_eager_attention_prefill_is_causal(patched):
+    """``_attn_implementation='eager'`` applies no mask unless it is given one: the patched forward must hand it an
+    explicit causal mask, i.e. produce the same hidden state and cache as the sdpa path."""
+    from transformers import LlamaConfig, LlamaForCausalLM
+    outs = []
+    for impl in ("sdpa", "eager"):
+        cfg = LlamaConfig(hidden_size=512, intermediate_size=1024, num_hidden_layers=2, num_attention_heads=8,
+                          num_key_value_heads=2, head_dim=64, vocab_size=211, max_position_embeddings=4096, attn_implementation=impl)
+        torch.manual_seed(0)
+        model = LlamaForCausalLM(cfg).eval().to(DEV)
+        patched.set_model(model, _args(tsp_idx=0))
+        ids = torch.randint(0, 211, (1, 500), generator=torch.Generator().manual_seed(8)).to(DEV)
+        with torch.no_grad():
+            out = model.model(ids, use_cache=True)
+        outs.append((out.last_hidden_state.cpu(), out.past_key_values.buffers(1)[0][:, :, :128].cpu()))
+    assert torch.allclose(outs[0][0], outs[1][0], atol=2e-3, rtol=1e-3)
+    assert torch.allclose(outs[0][1], outs[1][1], atol=2e-3, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# SnapKV at model level (baselines/snapkv/llama_model.py:385-404): prefill cache + greedy decode
+# ---------------------------------------------------------------------------------------------
+def test_snapkv_model_prefill_and_decode_match_glue_oracle(patched):
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    n, c, w = 512, 96, 16
+    ids = torch.randint(0, 211, (1, n), generator=torch.Generator().manual_seed(5))
+    knobs = [dict(window_size=w, max_capacity_prompt=c, kernel_size=5, pooling="avgpool") for _ in range(2)]
+    patched.replace_llama("fullkv")
+    model = _model(torch.float32, layers=2)
+    ref_hidden, ref_caches, traces = G.snapkv_prefill(model, ids, knobs, apply_rotary_pos_emb)
+    first = model.lm_head(ref_hidden)[:, -1].argmax(-1, keepdim=True)
+    # the reference's benchmark loop passes no position ids: decode continues from the compact length (e2e.py:174)
+    ref_toks, _ = G.decode_steps(model, ref_caches, first, c, 5, apply_rotary_pos_emb, expand_new_kv=True)
+    patched.replace_llama("snapkv")
+    gm = _model(torch.float32, layers=2).to(DEV)
+    patched.set_model(gm, _args(method="snapkv", window_size=w, kernel_size=5, max_capacity_prompts=c))
+    for layer in gm.model.layers:
+        layer.self_attn.kv_cluster.keep_aux = True
+    toks, cache = patched.greedy_generate(gm, ids.to(DEV), 6)
+    torch.cuda.synchronize()
+    for i in range(2):
+        kbuf, vbuf, nrows, _ = cache.buffers(i)
+        assert kbuf.shape[1] == 8 and nrows == c + 5                      # one cache head per QUERY head, every row written
+        _check_cache_rows(gm.model.layers[i].self_attn.kv_cluster.last_aux["idx"].cpu(), traces[i].idx,
+                          kbuf[:, :, :c].cpu(), vbuf[:, :, :c].cpu(), ref_caches[i][0], ref_caches[i][1], w)
+        # decode rows: all 8 heads hold the new token's K (head h = kv head h // 4), none is left uninitialised
+        new_rows = kbuf[:, :, c:nrows].cpu()
+        assert torch.isfinite(new_rows).all()
+        assert torch.equal(new_rows[:, 0], new_rows[:, 3]) and torch.equal(new_rows[:, 4], new_rows[:, 7])
+        assert not torch.equal(new_rows[:, 0], new_rows[:, 4])
+    assert toks[0, 0].item() == first.item()
+    assert torch.equal(toks[:, 1:].cpu(), ref_toks)
+
+
+# ---------------------------------------------------------------------------------------------
+# generate() path: positions continue from the TRUE prompt length (baselines/monkeypatch.py:280-288)
+# ---------------------------------------------------------------------------------------------
+def test_generate_positions_continue_from_the_true_prompt_length(patched):
+    from transformers.models.llama.modeling_llama import apply_rotary_pos_emb
+    n, new = 600, 8
+    ids = torch.randint(0, 211, (1, n), generator=torch.Generator().manual_seed(21))
+    knobs = [dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=(i == 1), tsp_length=256)
+             for i in range(3)]
+    patched.replace_llama("fullkv")
+    model = _model(torch.float32)
+    ref_hidden, ref_caches, _ = G.fastkv_prefill(model, ids, knobs, apply_rotary_pos_emb)
+    first = model.lm_head(ref_hidden)[:, -1].argmax(-1, keepdim=True)
+    ref_toks, ref_pos = G.decode_steps(model, [c[:2] for c in ref_caches], first, n, new - 1, apply_rotary_pos_emb)
+    assert ref_pos == list(range(n, n + new - 1))
+    patched.replace_llama("fastkv")
+    gm = _model(torch.float32).to(DEV)
+    gm.generation_config.pad_token_id = 0
+    patched.set_model(gm, _args())
+    seen = []
+    inner = gm.model.forward
+
+    def spy(*a, **kw):
+        seen.append(kw["position_ids"].flatten().tolist() if kw.get("position_ids") is not None else None)
+        return inner(*a, **kw)
+
+    gm.model.forward = spy
+    out = gm.generate(ids.to(DEV), attention_mask=torch.ones_like(ids).to(DEV), max_new_tokens=new, do_sample=False)
+    assert seen[0] == list(range(n))
+    assert [p[0] for p in seen[1:]] == list(range(n, n + new - 1))          # NOT 128 + t (the compact length)
+    assert torch.equal(out[0, n:].cpu(), torch.cat([first[0], ref_toks[0]]))

@@ -76,10 +76,15 @@ def test_fastkv_matches_reference_golden(name, dtype):
         else:
             flat = ref.score.reshape(-1, ref.score.shape[-1])
             check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), name)
-            # golden K/V: same rows as the reference wherever the index sets agree exactly
-            if torch.equal(aux["idx"].cpu(), ref.idx):
-                assert torch.equal(ko.cpu().to(torch.bfloat16), fx["key_out"])
-                assert torch.equal(vo.cpu().to(torch.bfloat16), fx["value_out"])
+            # golden K/V: the reference's rows at every position where the score-descending orders agree (near-tie
+            # swaps are the only tolerated difference), and the window rows always
+            same = aux["idx"].cpu() == ref.idx
+            assert same.float().mean().item() > 0.97, same.float().mean().item()
+            nsel = ref.idx.shape[-1]
+            assert torch.equal(ko.cpu().to(torch.bfloat16)[:, :, :nsel][same], fx["key_out"][:, :, :nsel][same])
+            assert torch.equal(vo.cpu().to(torch.bfloat16)[:, :, :nsel][same], fx["value_out"][:, :, :nsel][same])
+            assert torch.equal(ko.cpu().to(torch.bfloat16)[:, :, nsel:], fx["key_out"][:, :, nsel:])
+            assert torch.equal(vo.cpu().to(torch.bfloat16)[:, :, nsel:], fx["value_out"][:, :, nsel:])
         check_topk_consistent(aux["score"], aux["idx"], name)
         check_compaction_exact(k32.to(dtype), v32.to(dtype), aux["idx"], ko, vo, w)
         if ref.tsp_idx is None:
@@ -93,8 +98,10 @@ def test_fastkv_matches_reference_golden(name, dtype):
                 assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
             else:
                 check_selection(ref.importance, ref.tsp_idx[:, :-w], tsp[:, :-w], name + "/tsp")
-                if torch.equal(tsp.cpu(), ref.tsp_idx):
-                    assert torch.equal(tsp.cpu(), fx["tsp_idx"])
+                assert torch.equal(ref.tsp_idx, fx["tsp_idx"])               # the oracle is the pinned reference
+                for bi in range(tsp.shape[0]):                               # only near-tie members may differ
+                    assert len(set(tsp[bi].tolist()) ^ set(fx["tsp_idx"][bi].tolist())) <= max(2, tsp.shape[1] // 100)
+                assert torch.equal(tsp.cpu()[:, -w:], fx["tsp_idx"][:, -w:])
 
 
 def test_bf16_run_of_the_reference_is_within_bf16_tolerance():
@@ -135,8 +142,12 @@ def test_snapkv_matches_reference_golden(name, expanded):
     if knobs["pooling"] == "avgpool":
         flat = ref.score.reshape(-1, ref.score.shape[-1])
         check_selection(flat, ref.idx.reshape(flat.shape[0], -1), aux["idx"].reshape(flat.shape[0], -1), name)
-        if torch.equal(aux["idx"].cpu(), ref.idx):
-            assert torch.equal(ko.cpu(), fx["key_out"]) and torch.equal(vo.cpu(), fx["value_out"])
+        same = aux["idx"].cpu() == ref.idx
+        assert same.float().mean().item() > 0.97, same.float().mean().item()
+        nsel = ref.idx.shape[-1]
+        assert torch.equal(ko.cpu()[:, :, :nsel][same], fx["key_out"][:, :, :nsel][same])
+        assert torch.equal(vo.cpu()[:, :, :nsel][same], fx["value_out"][:, :, :nsel][same])
+        assert torch.equal(ko.cpu()[:, :, nsel:], fx["key_out"][:, :, nsel:]) and torch.equal(vo.cpu()[:, :, nsel:], fx["value_out"][:, :, nsel:])
 
 
 @pytest.mark.parametrize("name", golden_names("gemfilter"))
@@ -155,8 +166,8 @@ def test_gemfilter_matches_reference_golden(name):
     got = holder.indecies
     assert got.shape == ref_idx.shape
     check_selection(ref_scores[0], ref_idx[0], got[0], name)
-    if set(got[0, 0].tolist()) == set(ref_idx[0, 0].tolist()):
-        assert torch.equal(torch.sort(got[0, 0].cpu()).values, fx["sorted_indices"])
+    assert torch.equal(ref_sorted, fx["sorted_indices"])                     # the oracle is the pinned reference
+    assert len(set(got[0, 0].tolist()) ^ set(fx["sorted_indices"].tolist())) <= max(2, fx["topk"] // 100)
 
 
 @pytest.mark.parametrize("b,hq,hkv,l,d,ks", [(1, 32, 8, 5000, 128, 5), (2, 16, 4, 1234, 128, 5), (1, 8, 8, 700, 64, 5),
@@ -361,31 +372,77 @@ def test_scoring_kernel_phase_loop_at_small_sizes(ppp):
 
 
 # ---------------------------------------------------------------------------------------------
-# full BASELINE sizes: size-independent properties (the oracle would take minutes here)
+# the contract sizes (BASELINE.json configs[1..3]) against the pinned CPU oracle, full protocol
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("l,c,t,b", [(32768, 2048, 2048, 1), (131072, 2048, 2048, 1), (32768, 512, 2048, 2)])
-def test_full_size_properties(l, c, t, b):
+def _contract_inputs(seed, b, l, hq, hkv, d, dist):
+    """bf16 q/k/v generated on the GPU ([B,H,L,D] views of [B,L,H,D] memory, the call-site layout)."""
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    mk = lambda h: torch.randn(b, l, h, d, generator=g, device=DEV, dtype=torch.bfloat16)
+    q, k, v = mk(hq), mk(hkv), mk(hkv)
+    if dist == "peaky":                              # 1 % heavy-hitter tokens (SURVEY.md §8d)
+        hot = torch.rand(l, generator=g, device=DEV) < 0.01
+        k[:, hot] = (k[:, hot].float() * 4).to(torch.bfloat16)
+    elif dist == "ties":                             # K quantised to 4 distinct rows: exact score ties
+        rows = torch.randn(4, d, generator=g, device=DEV, dtype=torch.bfloat16)
+        k = rows[torch.randint(0, 4, (b, l, hkv), generator=g, device=DEV)]
+    return q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+
+
+CONTRACT = [
+    # L, C, T, B, dist
+    (32768, 2048, 2048, 1, "gauss"),                 # configs[1]: Llama-3.1-8B, 32k prefill, C = T = 2048
+    (32768, 2048, 2048, 1, "peaky"),
+    (32768, 2048, 2048, 1, "ties"),
+    (131072, 2048, 2048, 1, "gauss"),                # configs[2]: 128k prefill (4-phase TMEM-recycling path)
+    (32768, 512, 2048, 8, "gauss"),                  # configs[3]: Ministral-8B geometry, batch 8 x 32k, C = 512 (8 phases)
+]
+
+
+@pytest.mark.parametrize("l,c,t,b,dist", CONTRACT, ids=[f"L{x[0]}_C{x[1]}_B{x[3]}_{x[4]}" for x in CONTRACT])
+def test_contract_sizes_vs_oracle(l, c, t, b, dist):
+    """BASELINE configs[1..3] at their REAL sizes against the pinned oracle (fp32, CPU), full protocol: scores
+    <= 2e-5, per-head and TSP index sets equal up to the 1e-5 near-tie rule, K/V bit-exact given our indices and
+    equal to the oracle's rows wherever the indices agree."""
     hq, hkv, d, w = 32, 8, 128, 8
-    g = torch.Generator(device=DEV).manual_seed(l + c)
-    q = torch.randn(b, l, hq, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
-    k = torch.randn(b, l, hkv, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
-    v = torch.randn(b, l, hkv, d, generator=g, device=DEV, dtype=torch.bfloat16).transpose(1, 2)
+    q, k, v = _contract_inputs(l + c + b, b, l, hq, hkv, d, dist)
     knobs = dict(window_size=w, max_capacity_prompt=c, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=t)
     cl, (ko, vo, tsp) = _run_cluster(knobs, k, q, v, hq // hkv, _lib().IMPL_AUTO)
     aux = cl.last_aux
-    score = aux["score"]
-    assert score.shape == (b, hkv, l - w) and torch.isfinite(score).all() and (score >= 0).all()
-    # softmax rows sum to 1: total vote mass over the prefix is <= W per query head, pooled mass likewise
-    assert (score.sum(-1) <= (hq // hkv) * w * (1 + 1e-3)).all()
-    check_topk_consistent(score, aux["idx"])
-    check_tsp_consistent(aux["importance"], tsp, w)
-    imp = score.sum(dim=1)
-    assert torch.allclose(imp, aux["importance"], rtol=1e-5, atol=0)
+    assert _lib().load().fkv_score_impl_name is not None
+    assert ko.shape == (b, hkv, c, d) and tsp.shape == (b, t)
+    check_topk_consistent(aux["score"], aux["idx"], "contract")
+    check_tsp_consistent(aux["importance"], tsp, w, "contract")
     check_compaction_exact(k, v, aux["idx"], ko, vo, w)
-    assert (tsp[:, 1:] > tsp[:, :-1]).all() and tsp[:, -1].eq(l - 1).all()
-    # idempotence of the propagation: gathering with the TSP set keeps the window rows last
+    score, idx, imp = aux["score"].cpu(), aux["idx"].cpu(), aux["importance"].cpu()
+    ko_c, vo_c, tsp_c = ko.cpu(), vo.cpu(), tsp.cpu()
+    for bi in range(b):                               # one prompt at a time keeps the fp32 oracle's footprint small
+        ref = O.fastkv_update_kv(k[bi:bi + 1].cpu().float(), q[bi:bi + 1].cpu().float(), v[bi:bi + 1].cpu().float(),
+                                 hq // hkv, **knobs)
+        check_scores_close(ref.score, score[bi:bi + 1], SCORE_RTOL, f"contract b{bi}")
+        check_scores_close(ref.importance, imp[bi:bi + 1], SCORE_RTOL, f"contract importance b{bi}")
+        if dist == "ties":
+            # exact ties: the reference's tie order is unspecified -> the selected score multisets must agree
+            ours = torch.gather(ref.score[0], -1, idx[bi]).sort(-1).values
+            theirs = torch.gather(ref.score[0], -1, ref.idx[0]).sort(-1).values
+            assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+            ours = torch.gather(ref.importance[0], -1, tsp_c[bi, :-w]).sort(-1).values
+            theirs = torch.gather(ref.importance[0], -1, ref.tsp_idx[0, :-w]).sort(-1).values
+            assert torch.allclose(ours, theirs, rtol=1e-5, atol=0)
+            continue
+        check_selection(ref.score[0], ref.idx[0], idx[bi], f"contract b{bi}")
+        check_selection(ref.importance, ref.tsp_idx[:, :-w], tsp_c[bi:bi + 1, :-w], f"contract tsp b{bi}")
+        assert torch.equal(tsp_c[bi, -w:], ref.tsp_idx[0, -w:])
+        # cache layout: same rows as the reference at every position where the (score-descending) orders agree;
+        # continuous scores at these sizes leave at most a handful of near-tie swaps
+        same = idx[bi] == ref.idx[0]                                             # [Hkv, C-W]
+        assert same.float().mean().item() > 0.99, same.float().mean().item()
+        assert torch.equal(ko_c[bi, :, :c - w][same], ref.key[0, :, :c - w].to(torch.bfloat16)[same])
+        assert torch.equal(vo_c[bi, :, :c - w][same], ref.value[0, :, :c - w].to(torch.bfloat16)[same])
+        assert torch.equal(ko_c[bi, :, c - w:], ref.key[0, :, c - w:].to(torch.bfloat16))
+        assert torch.equal(vo_c[bi, :, c - w:], ref.value[0, :, c - w:].to(torch.bfloat16))
+    # propagation at the real size: hidden rows / position ids bit-exact for the selected set
     from fastkv_b200 import ops
-    hidden = torch.randn(b, l, 4096, generator=g, device=DEV, dtype=torch.bfloat16)
+    hidden = torch.randn(b, l, 4096, generator=torch.Generator(device=DEV).manual_seed(l), device=DEV, dtype=torch.bfloat16)
     pos = torch.arange(l, device=DEV).unsqueeze(0)
     nh, npos = ops.gather_rows(hidden, tsp, pos)
     assert torch.equal(npos, tsp)

@@ -148,3 +148,61 @@ def test_bench_reference_arm_contract():
         assert key in line, key
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["config"]["workload"]
+
+
+class _KeepFirstRows:
+    """Test double for the per-layer compressor (CPU tests cannot run the CUDA kernels): keeps the first C-W rows and
+    the W window rows, so the cache is COMPACT and the position rule of the generate() path can be checked."""
+    tsp_layer = False
+
+    def __init__(self, capacity=16, window=4):
+        self.c, self.w = capacity, window
+
+    def update_kv(self, k, q, v, attention_mask, groups, layer_idx=None):
+        if k.shape[2] < self.c:
+            return k, v, None
+        sel = lambda x: torch.cat([x[:, :, :self.c - self.w], x[:, :, -self.w:]], dim=2).contiguous()
+        return sel(k), sel(v), None
+
+
+@pytest.mark.parametrize("with_mask,own_cache", [(True, False), (False, True), (True, True)])
+def test_generate_path_positions_follow_the_true_length(patched, with_mask, own_cache):
+    """baselines/monkeypatch.py:280-288: decode position ids continue from the true prompt length although the cache
+    holds only the compacted rows — from the attention mask when there is one, else from CompactKVCache.true_length."""
+    from fastkv_b200.cache import CompactKVCache
+    model = _tiny_llama()
+    model.generation_config.pad_token_id = 0
+    patched.set_model(model, _args())
+    for layer in model.model.layers:
+        layer.self_attn.kv_cluster = _KeepFirstRows()
+    n, new = 40, 5
+    ids = torch.randint(1, 97, (1, n), generator=torch.Generator().manual_seed(2))
+    seen, inner = [], model.model.forward
+
+    def spy(*a, **kw):
+        pos = kw.get("position_ids")
+        seen.append(None if pos is None else pos.flatten().tolist())
+        return inner(*a, **kw)
+
+    model.model.forward = spy
+    kw = {}
+    if with_mask:
+        kw["attention_mask"] = torch.ones_like(ids)
+    cache = CompactKVCache(model.config, max_new_tokens=8) if own_cache else None
+    if own_cache:
+        kw["past_key_values"] = cache
+    if with_mask:
+        out = model.generate(ids, max_new_tokens=new, do_sample=False, **kw)
+        assert out.shape == (1, n + new)
+    else:
+        # no mask: drive prepare_inputs_for_generation by hand, like a custom loop would
+        with torch.no_grad():
+            cur = ids
+            for _ in range(new):
+                inputs = model.prepare_inputs_for_generation(cur, past_key_values=cache, use_cache=True)
+                logits = model(**inputs).logits
+                cur = torch.cat([cur, logits[:, -1].argmax(-1, keepdim=True)], dim=1)
+    assert seen[0] is None or seen[0] == list(range(n))
+    assert [p[-1] for p in seen[1:]] == list(range(n, n + new - 1)), seen[1:]
+    if own_cache:
+        assert cache.get_seq_length() == 16 + new - 1 and cache.true_length == n + new - 1
