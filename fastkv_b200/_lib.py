@@ -223,13 +223,13 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
            torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        buf = torch.empty(max(nbytes, 8 << 20), dtype=torch.uint8, device=device)
         check(load().fkv_workspace_init(buf.data_ptr(), buf.numel(), torch.cuda.current_stream(device).cuda_stream))
         _workspaces[key] = buf
     return buf
 
 
-WS_HEADER = 256   # FKV_WORKSPACE_HEADER_BYTES: the scoring kernel's departure counter + launch epoch + error word
+WS_HEADER = 256 + 128 * 32 + 2 * 128 * 4096 * 4   # FKV_WORKSPACE_HEADER_BYTES: the library's persistent region
 
 
 def scratch(device: torch.device, nbytes: int):

@@ -122,12 +122,16 @@ int validate_score(const fkv_score_params& p) {
   return FKV_OK;
 }
 
-int run_score(const fkv_score_params& p, cudaStream_t s) {
+// *hist_used: whether the scoring kernel filled the optional histogram table (tensor path only)
+int run_score(const fkv_score_params& p, cudaStream_t s, bool want_hist = false, bool* hist_used = nullptr) {
   int impl = p.impl;
+  if (hist_used) *hist_used = false;
   if (impl == FKV_IMPL_AUTO) impl = score_tensor_supported(p) ? FKV_IMPL_TENSOR : FKV_IMPL_SIMPLE;
   if (impl == FKV_IMPL_TENSOR) {
     if (!score_tensor_supported(p)) return FKV_EMODE;
-    return launch_score_tensor(p, s);
+    const bool with_hist = want_hist && p.mode != FKV_MODE_GEMFILTER && p.B * (p.h1 - p.h0) <= kHistMaxRows;
+    if (hist_used) *hist_used = with_hist;
+    return launch_score_tensor(p, s, with_hist);
   }
   return launch_score_simple(p, s);
 }
@@ -168,6 +172,7 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
   const int k_head = capacity > window_size ? capacity - window_size : 1;
   b += topk_workspace_bytes(B * Hsel, L, k_head);
   if (tsp_k > 0) b += topk_workspace_bytes(B, L, tsp_k);
+  b += select_scratch_bytes(B * Hsel);
   return b + 4096;                                     // score_workspace_bytes already includes the header
 }
 
@@ -301,14 +306,13 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   const size_t score_ws = score_workspace_bytes(sp.mode, sp.B, sp.Hq, sp.Hkv, sp.L, W);
   const size_t head_ws = topk_workspace_bytes(sp.B * Hsel, P, n_sel);
   const size_t tsp_ws = p->tsp_k > 0 ? topk_workspace_bytes(sp.B, P, p->tsp_k) : 0;
-  if (sp.workspace_bytes < score_ws + head_ws + tsp_ws) return FKV_EWORKSPACE;
+  const size_t sel_ws = select_scratch_bytes(sp.B * Hsel);
+  if (sp.workspace_bytes < score_ws + head_ws + tsp_ws + sel_ws) return FKV_EWORKSPACE;
   char* ws = reinterpret_cast<char*>(sp.workspace);
   cudaStream_t s = (cudaStream_t)stream;
 
   // short contexts (post-TSP layers): score + top-k + compaction in one cluster kernel
   if (small_compress_supported(*p)) return launch_small_compress(*p, s);
-
-  if ((rc = run_score(sp, s)) != FKV_OK) return rc;
 
   // per-head top-k needs rows addressed as one flat list: require the dense [B,Hsel,P] layout
   if (sp.score_stride_h != P || sp.score_stride_b != (int64_t)Hsel * P) return FKV_EINVAL;
@@ -324,8 +328,15 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   g.h0 = sp.h0; g.h1 = sp.h1; g.head_div = sp.mode == FKV_MODE_SNAPKV ? sp.Hq / sp.Hkv : 1;
   g.k = sp.k; g.v = p->v; g.idx = p->idx_out; g.idx_stride_b = (int64_t)Hsel * n_sel; g.idx_stride_h = n_sel;
   g.k_out = p->k_out; g.v_out = p->v_out;
+  // K1+K2, building the per-row 12-bit histogram on the way when the fused select + compact kernel will consume it
+  const bool use_select = select_compact_supported(tk, g);
+  bool hist_used = false;
+  if ((rc = run_score(sp, s, use_select && P > 4096, &hist_used)) != FKV_OK) return rc;   // short rows need no histogram
   bool fused = false;
-  if ((rc = launch_topk_fused(tk, g, &fused, s)) != FKV_OK) return rc;     // K3 (+ K4 when the cluster kernel runs)
+  if (use_select) {                                                         // K3 + K4 in one launch
+    if ((rc = launch_select_compact(tk, g, ws, ws + score_ws + head_ws + tsp_ws, hist_used, s)) != FKV_OK) return rc;
+    fused = true;
+  } else if ((rc = launch_topk_fused(tk, g, &fused, s)) != FKV_OK) return rc;   // K3 (+ K4 when the cluster kernel runs)
 
   if (p->tsp_k > 0) {
     fkv_topk_params tt{};

@@ -263,7 +263,7 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
     if ((rc_attr = ensure_dyn_smem(score_tile_kernel<T, kVotes>, smem_max)) != FKV_OK) return rc_attr;
     if ((rc_attr = ensure_dyn_smem(score_tile_kernel<T, kRaw>, smem_max)) != FKV_OK) return rc_attr;
   }
-  char* ws = reinterpret_cast<char*>(p.workspace) + 256;   // the first 256 bytes hold the tensor path's barrier counters
+  char* ws = reinterpret_cast<char*>(p.workspace) + FKV_WORKSPACE_HEADER_BYTES;   // past the library's persistent region
 
   if (p.mode == FKV_MODE_GEMFILTER) {
     const int qh0 = p.qh0, qh1 = (p.qh1 > p.qh0) ? p.qh1 : p.Hq;
@@ -313,14 +313,14 @@ int run_simple(const fkv_score_params& p, cudaStream_t s) {
 // Scratch for the simple path (also an upper bound for the tensor path, which needs less).
 size_t score_workspace_bytes(int mode, int B, int Hq, int Hkv, int L, int W) {
   const int n_tiles = ceil_div(L, kTileKeys);
-  if (mode == FKV_MODE_GEMFILTER) return 256 + align_up((size_t)B * Hq * L * sizeof(float), 256);
+  if (mode == FKV_MODE_GEMFILTER) return FKV_WORKSPACE_HEADER_BYTES + align_up((size_t)B * Hq * L * sizeof(float), 256);
   const int Hsel = (mode == FKV_MODE_FASTKV) ? Hkv : Hq;
   const int G = (mode == FKV_MODE_FASTKV) ? Hq / Hkv : 1;
   size_t b = 0;
   b = align_up(b + (size_t)B * Hsel * n_tiles * G * W * sizeof(float2), 256);
   b = align_up(b + (size_t)B * Hsel * G * W * sizeof(float2), 256);
   b = align_up(b + (size_t)B * Hsel * G * (size_t)L * sizeof(float), 256);
-  return b + 1024 + 256;
+  return b + 1024 + FKV_WORKSPACE_HEADER_BYTES;
 }
 
 int launch_score_simple(const fkv_score_params& p, cudaStream_t s) {

@@ -36,7 +36,23 @@ struct TcArgs {
   unsigned int* sync_counter;                           // workspace header: [1] departures (left zero), u64 at [2] = launch epoch
   unsigned long long* trace;                            // optional [grid][16] globaltimer stamps (FKV_TC_TRACE=1)
   float* score; int64_t score_sb, score_sh; int out_h0;
+  unsigned int* hist;                                   // optional [B * hist_hpb][4096] 12-bit histogram of the stored scores
+  int hist_hpb;                                         // selection heads per batch element in that table
 };
+
+// order-preserving key of a score (same map as topk_common.cuh) -> its 12-bit histogram bin
+__device__ __forceinline__ uint32_t score_bin(float x) {
+  x += 0.0f;
+  const uint32_t u = __float_as_uint(x);
+  return ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) >> 20;
+}
+// one RED per distinct bin of the warp: pooled scores of neighbouring keys mostly share a 1/8-octave bin
+__device__ __forceinline__ void hist_red(unsigned int* hrow, float score, bool valid) {
+  const uint32_t bin = valid ? score_bin(score) : 0xffffffffu;
+  const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+  if (valid && (int)(threadIdx.x & 31) == __ffs(peers) - 1)
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(hrow + bin), "r"((uint32_t)__popc(peers)) : "memory");
+}
 
 // kDef: the reference's default epilogue (avgpool, kernel_size 7, FastKV group-sum, single head group) compiled
 // without the other variants, so the pass-2 loop stays small and contiguous in the instruction cache
@@ -424,9 +440,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       }
       named_bar(3 + wg, 128);
       const bool own = (row >= a.half) && (row < a.half + a.S) && in_prefix;
-      if (own) {
-        if constexpr (kDef) {
-          float acc = 0.f;
+      if constexpr (kDef) {
+        float acc = 0.f;
+        if (own) {
 #pragma unroll
           for (int g = 0; g < G; ++g) {
             const float* vr = vb + g * kTile + row;
@@ -436,9 +452,14 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
             acc += sum * inv_ks;                      // avg_pool1d (count_include_pad), GQA group-sum with g in order
           }
           a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
-        } else {
+        }
+        if (a.hist) hist_red(a.hist + (size_t)(b * a.hist_hpb + a.kv0 + kvl - a.out_h0) * 4096, acc, own);
+      } else {
+        float pooled_g[G];
+        float acc = 0.f;
+        if (own) {
           // a later head sub-group continues the sum of the earlier launches: ((p0 + p1) + p2) + p3 as in utils.py:112
-          float acc = a.accumulate ? a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] : 0.f;
+          acc = a.accumulate ? a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] : 0.f;
   #pragma unroll
           for (int g = 0; g < G; ++g) {
             float pooled;
@@ -459,10 +480,20 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
               }
               pooled = sum * inv_ks;                    // count_include_pad: always / kernel_size
             }
+            pooled_g[g] = pooled;
             if (a.group_sum) acc += pooled;             // GQA group-sum, g in order (utils.py:112)
             else a.score[(int64_t)b * a.score_sb + (int64_t)((a.kv0 + kvl) * a.q_heads_per_kv + a.g0 + g - a.out_h0) * a.score_sh + key] = pooled;
           }
           if (a.group_sum) a.score[(int64_t)b * a.score_sb + (int64_t)(a.kv0 + kvl - a.out_h0) * a.score_sh + key] = acc;
+        }
+        if (a.hist) {                                  // warp-uniform: the match below needs all 32 lanes
+          if (a.group_sum) hist_red(a.hist + (size_t)(b * a.hist_hpb + a.kv0 + kvl - a.out_h0) * 4096, acc, own);
+          else {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              hist_red(a.hist + (size_t)(b * a.hist_hpb + (a.kv0 + kvl) * a.q_heads_per_kv + a.g0 + g - a.out_h0) * 4096,
+                       own ? pooled_g[g] : 0.f, own);
+          }
         }
       }
       t += kNumWG;
@@ -589,11 +620,12 @@ bool score_tensor_supported(const fkv_score_params& p) {
   return p.mode == FKV_MODE_GEMFILTER ? gemfilter_tensor_supported(p) : make_plan(p).ok;
 }
 
-int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
+int launch_score_tensor(const fkv_score_params& p, cudaStream_t s, bool with_hist) {
   if (p.mode == FKV_MODE_GEMFILTER) return launch_score_gemfilter(p, s);
   const Plan pl = make_plan(p);
   if (!pl.ok) return FKV_EMODE;
-  if (p.workspace_bytes < pl.part_bytes + 256) return FKV_EWORKSPACE;
+  if (p.workspace_bytes < pl.part_bytes + FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
+  if (with_hist && p.B * (p.h1 - p.h0) > kHistMaxRows) return FKV_EINVAL;
   TcArgs a{};
   a.B = p.B; a.L = p.L; a.P = p.L - p.window_size; a.D = p.D;
   a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
@@ -603,7 +635,8 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   a.c = (1.0f / sqrtf((float)p.D)) * 1.4426950408889634f;
   char* ws = reinterpret_cast<char*>(p.workspace);
   a.sync_counter = reinterpret_cast<unsigned int*>(ws);
-  a.part = reinterpret_cast<unsigned long long*>(ws + 256);
+  a.part = reinterpret_cast<unsigned long long*>(ws + FKV_WORKSPACE_HEADER_BYTES);
+  void* hist = with_hist ? ws + kWsHistOffset : nullptr;
   a.score = p.score; a.score_sb = p.score_stride_b; a.score_sh = p.score_stride_h; a.out_h0 = p.h0;
 
   CUtensorMap mk, mq;
@@ -623,6 +656,9 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
   for (int g0 = 0; g0 < pl.Gm; g0 += pl.G) {         // one launch per head sub-group (a single one for W*G <= 32)
     a.g0 = g0;
     a.accumulate = (a.group_sum && g0 > 0) ? 1 : 0;
+    // the histogram counts FINAL scores: with a group sum spread over several launches only the last one adds to it
+    a.hist = (hist && (!a.group_sum || g0 + pl.G >= pl.Gm)) ? reinterpret_cast<unsigned int*>(hist) : nullptr;
+    a.hist_hpb = p.h1 - p.h0;
     const bool def_epi = a.group_sum && !a.accumulate && a.pooling == FKV_POOL_AVG && a.half == 3;
     FKV_TC_CASE(8, 1); FKV_TC_CASE(8, 2); FKV_TC_CASE(8, 4);
     FKV_TC_CASE(16, 1); FKV_TC_CASE(16, 2);

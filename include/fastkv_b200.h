@@ -24,12 +24,13 @@ extern "C" {
 #define FKV_ABI_VERSION 4
 
 /* Every `workspace` argument below is one kind of buffer: device memory, 256-byte aligned, passed ONCE through
- * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state of the scoring kernel (launch
- * epoch, departure counter, error word); every entry point that uses a workspace as scratch (fkv_topk,
- * fkv_decode_attn, the top-k stages of fkv_compress) starts PAST that header by itself, so one buffer can be
- * shared by all calls issued on a stream and no caller ever has to offset a pointer.  The *_workspace_bytes
- * queries include the header. */
-#define FKV_WORKSPACE_HEADER_BYTES 256
+ * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state owned by the library: 256 bytes
+ * for the scoring kernel (launch epoch, departure counter, error word), 128 x 32 bytes of per-score-row barrier
+ * counters and 2 x 128 score-row histograms of 4096 bins (first level filled by the scoring kernel, second level by
+ * the select + compact kernel, which consumes both and leaves everything zeroed again).
+ * Every entry point starts its own scratch PAST that region by itself, so one buffer can be shared by all calls
+ * issued on a stream and no caller ever has to offset a pointer.  The *_workspace_bytes queries include it. */
+#define FKV_WORKSPACE_HEADER_BYTES (256 + 128 * 32 + 2 * 128 * 4096 * 4)
 
 /* ---- enums ------------------------------------------------------------------------------- */
 enum { FKV_BF16 = 0, FKV_F16 = 1, FKV_F32 = 2 };                 /* element type of Q/K/V/hidden   */
