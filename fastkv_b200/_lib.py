@@ -39,6 +39,7 @@ class ScoreParams(C.Structure):
         ("q", View4), ("k", View4),
         ("score", C.c_void_p), ("score_stride_b", C.c_int64), ("score_stride_h", C.c_int64),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("hist_slot", C.c_int32), ("max_ctas", C.c_int32),
     ]
 
 
@@ -60,6 +61,16 @@ class GatherKvParams(C.Structure):
         ("k", View4), ("v", View4),
         ("idx", C.c_void_p), ("idx_stride_b", C.c_int64), ("idx_stride_h", C.c_int64),
         ("k_out", View4), ("v_out", View4),
+    ]
+
+
+class SelectCompactParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("hist_slot", C.c_int32), ("have_hist", C.c_int32),
+        ("score", C.c_void_p), ("idx_out", C.c_void_p),
+        ("gather", GatherKvParams),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("max_ctas", C.c_int32),
     ]
 
 
@@ -113,7 +124,8 @@ EXPORTS = [
     "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_workspace_status",
     "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
     "fkv_score_impl_name", "fkv_launch_count",
-    "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append", "fkv_compress",
+    "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_select_compact", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append",
+    "fkv_compress",
 ]
 
 _lib = None
@@ -151,6 +163,7 @@ def load():
         lib.fkv_score_impl_name.restype = C.c_char_p
         lib.fkv_score_impl_name.argtypes = [C.POINTER(ScoreParams)]
         for name, st in [("fkv_score", ScoreParams), ("fkv_topk", TopkParams), ("fkv_gather_kv", GatherKvParams),
+                         ("fkv_select_compact", SelectCompactParams),
                          ("fkv_gather_rows", GatherRowsParams), ("fkv_decode_attn", DecodeAttnParams),
                          ("fkv_cache_append", CacheAppendParams), ("fkv_compress", CompressParams)]:
             fn = getattr(lib, name)
@@ -223,13 +236,14 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
            torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 8 << 20), dtype=torch.uint8, device=device)
+        buf = torch.empty(max(nbytes, 16 << 20), dtype=torch.uint8, device=device)
         check(load().fkv_workspace_init(buf.data_ptr(), buf.numel(), torch.cuda.current_stream(device).cuda_stream))
         _workspaces[key] = buf
     return buf
 
 
-WS_HEADER = 256 + 128 * 32 + 2 * 128 * 4096 * 4   # FKV_WORKSPACE_HEADER_BYTES: the library's persistent region
+SELECT_MAX_ROWS = 64
+WS_HEADER = 256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8   # FKV_WORKSPACE_HEADER_BYTES: the library's persistent region
 
 
 def scratch(device: torch.device, nbytes: int):

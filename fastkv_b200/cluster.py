@@ -42,6 +42,9 @@ class FastKVCluster:
         # optional callable (batch, kv_heads, rows, head_dim, dtype, device) -> (k_buf, v_buf) [B,Hkv,rows,D] views:
         # the compaction kernel then writes straight into the caller's cache slot
         self.out_provider = None
+        # optional ops.SelectOverlap: the select + compact stage runs on its side stream and the returned K/V are
+        # complete only after overlap.join() (the model glue joins at the end of the prefill, bench.py at the end of a step)
+        self.overlap = None
 
     def reset(self, window_size=8, max_capacity_prompt=512, kernel_size=7, pooling='avgpool', tsp_layer=False,
               tsp_length=2048, tsp_rate=0.25, retain_rate=0.25, eviction_mode="constant"):
@@ -109,7 +112,7 @@ class FastKVCluster:
                                kernel_size=self.kernel_size, pooling=self.pooling,
                                capacity=self.max_capacity_prompt, tsp_len=self.tsp_length if want_tsp else 0,
                                mode=L.MODE_FASTKV, impl=self.score_impl, return_aux=self.keep_aux,
-                               k_out=k_dst, v_out=v_dst)
+                               k_out=k_dst, v_out=v_dst, overlap=None if host_io else self.overlap)
             k, v, tsp = res[0], res[1], res[2]
             if self.keep_aux:
                 self.last_aux = res[3]
@@ -125,7 +128,7 @@ class FastKVCluster:
         k, v, _, aux = ops.compress(query_states, key_states, value_states, window_size=w,
                                     kernel_size=self.kernel_size, pooling=self.pooling,
                                     capacity=self.max_capacity_prompt, tsp_len=0, mode=L.MODE_FASTKV,
-                                    impl=self.score_impl, return_aux=True)
+                                    impl=self.score_impl, return_aux=True, overlap=self.overlap)
         tsp, imp = self.shard.global_tsp(aux["score"], self.tsp_length - w, w)
         if self.keep_aux:
             aux["importance"] = imp
@@ -179,6 +182,7 @@ class SnapKVCluster:
         self.score_impl = L.IMPL_AUTO
         self.keep_aux = False
         self.last_aux = None
+        self.overlap = None                     # see FastKVCluster.overlap
 
     def reset(self, window_size=64, max_capacity_prompt=256 + 64, kernel_size=5, pooling='avgpool', merge=None,
               retain_rate=0.25, eviction_mode="constant"):
@@ -209,7 +213,7 @@ class SnapKVCluster:
         mode = L.MODE_FASTKV if expanded else L.MODE_SNAPKV
         res = ops.compress(query_states, key_states, value_states, window_size=self.window_size,
                            kernel_size=self.kernel_size, pooling=self.pooling, capacity=self.max_capacity_prompt,
-                           tsp_len=0, mode=mode, impl=self.score_impl, return_aux=self.keep_aux)
+                           tsp_len=0, mode=mode, impl=self.score_impl, return_aux=self.keep_aux, overlap=self.overlap)
         if self.keep_aux:
             self.last_aux = res[3]
         return res[0], res[1]

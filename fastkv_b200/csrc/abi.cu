@@ -119,19 +119,21 @@ int validate_score(const fkv_score_params& p) {
   // the header (launch epoch, departure counter) is persistent state: refuse a buffer that never went through
   // fkv_workspace_init instead of computing on a garbage epoch (no device-side trap, nothing is launched)
   if (!workspace_registered(p.workspace, FKV_WORKSPACE_HEADER_BYTES)) return FKV_EWORKSPACE;
+  if (p.hist_slot < 0 || p.hist_slot > kHistSlots || p.max_ctas < 0) return FKV_EINVAL;
   return FKV_OK;
 }
 
 // *hist_used: whether the scoring kernel filled the optional histogram table (tensor path only)
-int run_score(const fkv_score_params& p, cudaStream_t s, bool want_hist = false, bool* hist_used = nullptr) {
+int run_score(const fkv_score_params& p, cudaStream_t s, bool* hist_used = nullptr) {
   int impl = p.impl;
   if (hist_used) *hist_used = false;
   if (impl == FKV_IMPL_AUTO) impl = score_tensor_supported(p) ? FKV_IMPL_TENSOR : FKV_IMPL_SIMPLE;
   if (impl == FKV_IMPL_TENSOR) {
     if (!score_tensor_supported(p)) return FKV_EMODE;
-    const bool with_hist = want_hist && p.mode != FKV_MODE_GEMFILTER && p.B * (p.h1 - p.h0) <= kHistMaxRows;
-    if (hist_used) *hist_used = with_hist;
-    return launch_score_tensor(p, s, with_hist);
+    if (hist_used)
+      *hist_used = p.hist_slot >= 1 && p.hist_slot <= kHistSlots && p.mode != FKV_MODE_GEMFILTER &&
+                   p.B * (p.h1 - p.h0) <= kHistMaxRows;
+    return launch_score_tensor(p, s);
   }
   return launch_score_simple(p, s);
 }
@@ -172,7 +174,6 @@ size_t fkv_workspace_bytes(int32_t mode, int32_t B, int32_t Hq, int32_t Hkv, int
   const int k_head = capacity > window_size ? capacity - window_size : 1;
   b += topk_workspace_bytes(B * Hsel, L, k_head);
   if (tsp_k > 0) b += topk_workspace_bytes(B, L, tsp_k);
-  b += select_scratch_bytes(B * Hsel);
   return b + 4096;                                     // score_workspace_bytes already includes the header
 }
 
@@ -244,6 +245,35 @@ int fkv_gather_kv(const fkv_gather_kv_params* p, void* stream) {
   return launch_gather_kv(*p, (cudaStream_t)stream);
 }
 
+int fkv_select_compact(const fkv_select_compact_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_select_compact_params)) return FKV_EINVAL;
+  const fkv_gather_kv_params& g = p->gather;
+  if (g.struct_size != sizeof(fkv_gather_kv_params)) return FKV_EINVAL;
+  if (g.dtype < FKV_BF16 || g.dtype > FKV_F32) return FKV_EDTYPE;
+  if (g.D != 64 && g.D != 128) return FKV_EHEADDIM;
+  if (g.B < 1 || g.L < 1 || g.n_sel < 1 || g.window_size < 0 || g.h1 <= g.h0 || g.head_div < 1 || !p->score || !p->idx_out)
+    return FKV_EINVAL;
+  if (g.window_size >= g.L) return FKV_EWINDOW;
+  const int P = g.L - g.window_size, Hsel = g.h1 - g.h0;
+  if (g.n_sel > P) return FKV_ETOPK;
+  if (p->hist_slot < 1 || p->hist_slot > kHistSlots) return FKV_EINVAL;
+  const int es = dtype_size(g.dtype);
+  int rc;
+  if ((rc = check_view(g.k, es)) || (rc = check_view(g.v, es)) || (rc = check_view(g.k_out, es)) || (rc = check_view(g.v_out, es)))
+    return rc;
+  if (!p->workspace || p->workspace_bytes < FKV_WORKSPACE_HEADER_BYTES ||
+      !workspace_registered(p->workspace, FKV_WORKSPACE_HEADER_BYTES))
+    return FKV_EWORKSPACE;
+  fkv_topk_params tk{};
+  tk.struct_size = sizeof(tk);
+  tk.rows = g.B * Hsel; tk.n = P; tk.k = g.n_sel; tk.order = FKV_ORDER_VALUE_DESC; tk.tail = 0; tk.nsum = 1;
+  tk.src = p->score; tk.src_stride_row = P; tk.src_stride_sum = 0;
+  tk.out = p->idx_out; tk.out_stride_row = g.n_sel;
+  if (!select_compact_supported(tk, g)) return FKV_EMODE;
+  return launch_select_compact(tk, g, p->workspace, p->hist_slot, p->have_hist != 0 && P > 4096, (cudaStream_t)stream,
+                               p->max_ctas);
+}
+
 int fkv_gather_rows(const fkv_gather_rows_params* p, void* stream) {
   if (!p || p->struct_size != sizeof(fkv_gather_rows_params)) return FKV_EINVAL;
   if (p->B < 1 || p->L < 1 || p->T < 1 || !p->src || !p->out || !p->idx) return FKV_EINVAL;
@@ -306,8 +336,7 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   const size_t score_ws = score_workspace_bytes(sp.mode, sp.B, sp.Hq, sp.Hkv, sp.L, W);
   const size_t head_ws = topk_workspace_bytes(sp.B * Hsel, P, n_sel);
   const size_t tsp_ws = p->tsp_k > 0 ? topk_workspace_bytes(sp.B, P, p->tsp_k) : 0;
-  const size_t sel_ws = select_scratch_bytes(sp.B * Hsel);
-  if (sp.workspace_bytes < score_ws + head_ws + tsp_ws + sel_ws) return FKV_EWORKSPACE;
+  if (sp.workspace_bytes < score_ws + head_ws + tsp_ws) return FKV_EWORKSPACE;
   char* ws = reinterpret_cast<char*>(sp.workspace);
   cudaStream_t s = (cudaStream_t)stream;
 
@@ -331,10 +360,13 @@ int fkv_compress(const fkv_compress_params* p, void* stream) {
   // K1+K2, building the per-row 12-bit histogram on the way when the fused select + compact kernel will consume it
   const bool use_select = select_compact_supported(tk, g);
   bool hist_used = false;
-  if ((rc = run_score(sp, s, use_select && P > 4096, &hist_used)) != FKV_OK) return rc;   // short rows need no histogram
+  fkv_score_params sp2 = sp;
+  const int slot = (sp.hist_slot >= 1 && sp.hist_slot <= kHistSlots) ? sp.hist_slot : 1;
+  sp2.hist_slot = (use_select && P > 4096) ? slot : 0;                      // short rows need no histogram
+  if ((rc = run_score(sp2, s, &hist_used)) != FKV_OK) return rc;
   bool fused = false;
   if (use_select) {                                                         // K3 + K4 in one launch
-    if ((rc = launch_select_compact(tk, g, ws, ws + score_ws + head_ws + tsp_ws, hist_used, s)) != FKV_OK) return rc;
+    if ((rc = launch_select_compact(tk, g, ws, slot, hist_used, s)) != FKV_OK) return rc;
     fused = true;
   } else if ((rc = launch_topk_fused(tk, g, &fused, s)) != FKV_OK) return rc;   // K3 (+ K4 when the cluster kernel runs)
 

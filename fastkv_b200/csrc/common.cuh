@@ -35,11 +35,14 @@ __host__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a
 inline int dtype_size(int dtype) { return dtype == FKV_F32 ? 4 : 2; }
 
 // layout of the persistent region at the front of every workspace (FKV_WORKSPACE_HEADER_BYTES in the public header)
-constexpr int kHistMaxRows = 128;                                  // score rows (B * selection heads) served by the select + compact kernel
-constexpr size_t kWsCtlOffset = 256;                               // u32[kHistMaxRows][8]: per-row barrier counters / list cursor
-constexpr size_t kWsHistOffset = kWsCtlOffset + kHistMaxRows * 32; // u32[kHistMaxRows][4096]: 12-bit histogram of a score row
-constexpr size_t kWsSubHistOffset = kWsHistOffset + (size_t)kHistMaxRows * 4096 * 4;   // same, second level (threshold bin)
-static_assert(kWsSubHistOffset + (size_t)kHistMaxRows * 4096 * 4 == FKV_WORKSPACE_HEADER_BYTES, "workspace header layout");
+constexpr int kHistMaxRows = FKV_SELECT_MAX_ROWS;                  // score rows (B * selection heads) per slot
+constexpr int kHistSlots = 2;
+constexpr int kHistTotalRows = kHistSlots * kHistMaxRows;          // a slot's rows are [(slot-1) * kHistMaxRows, slot * kHistMaxRows)
+constexpr size_t kWsCtlOffset = 256;                               // u32[rows][8]: per-row barrier counters / list cursor
+constexpr size_t kWsHistOffset = kWsCtlOffset + kHistTotalRows * 32;                      // u32[rows][4096]: 12-bit histogram of a score row
+constexpr size_t kWsSubHistOffset = kWsHistOffset + (size_t)kHistTotalRows * 4096 * 4;    // same, second level (threshold bin)
+constexpr size_t kWsListOffset = kWsSubHistOffset + (size_t)kHistTotalRows * 4096 * 4;    // u64[rows][4096]: candidate lists
+static_assert(kWsListOffset + (size_t)kHistTotalRows * 4096 * 8 == FKV_WORKSPACE_HEADER_BYTES, "workspace header layout");
 
 constexpr uint32_t kWorkspaceMagic = 0xF457CB20u;   // written at byte 16 of a workspace by fkv_workspace_init
 
@@ -148,9 +151,9 @@ __device__ inline void st_stream16(void* p, const uint4& v) {
 // ---- per-file launchers (each .cu implements its own; abi.cu validates and dispatches) -----
 namespace fkv {
 int launch_score_simple(const fkv_score_params& p, cudaStream_t s);
-// with_hist: also add the 12-bit histogram of every stored score to the workspace's histogram region
+// p.hist_slot 1 / 2: also add the 12-bit histogram of every stored score to that slot's tables in the workspace
 // (B * (h1 - h0) <= kHistMaxRows rows, consumed and re-zeroed by launch_select_compact)
-int launch_score_tensor(const fkv_score_params& p, cudaStream_t s, bool with_hist = false);
+int launch_score_tensor(const fkv_score_params& p, cudaStream_t s);
 bool score_tensor_supported(const fkv_score_params& p);
 bool gemfilter_tensor_supported(const fkv_score_params& p);     // gemfilter_tc.cu
 int launch_score_gemfilter(const fkv_score_params& p, cudaStream_t s);
@@ -163,9 +166,8 @@ int launch_topk_fused(const fkv_topk_params& p, const fkv_gather_kv_params& g, b
 size_t topk_workspace_bytes(int rows, int n, int k);
 // select_compact.cu: per-head top-k + KV compaction in one non-cluster launch (consumes the producer-built histogram)
 bool select_compact_supported(const fkv_topk_params& p, const fkv_gather_kv_params& g);
-int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& g, void* workspace, void* scratch,
-                          bool have_hist, cudaStream_t s);
-size_t select_scratch_bytes(int rows);
+int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& g, void* workspace, int slot,
+                          bool have_hist, cudaStream_t s, int max_ctas = 0);
 int launch_gather_kv(const fkv_gather_kv_params& p, cudaStream_t s);
 int launch_gather_rows(const fkv_gather_rows_params& p, cudaStream_t s);
 int launch_decode_attn(const fkv_decode_attn_params& p, cudaStream_t s);

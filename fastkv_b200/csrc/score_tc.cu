@@ -555,7 +555,10 @@ Plan make_plan(const fkv_score_params& p) {
   const long long U = (long long)p.B * pl.nkv * pl.n_tiles;
   if (U * num_sms() >= (1ll << 31)) return pl;        // the kernel splits units with 32-bit arithmetic
   pl.U = (int)U;
-  pl.grid = (int)(U < num_sms() ? U : num_sms());
+  static const int env_grid = getenv("FKV_TC_GRID") ? atoi(getenv("FKV_TC_GRID")) : 0;   // experiments: leave SMs to a concurrent kernel
+  int sms = (env_grid > 0 && env_grid < num_sms()) ? env_grid : num_sms();
+  if (p.max_ctas > 0 && p.max_ctas < sms) sms = p.max_ctas;
+  pl.grid = (int)(U < sms ? U : sms);
   // phases: groups of `ppp` (b, h) pairs whose tiles fit in the TMEM blocks of the CTAs (<= NB tiles per
   // CTA and phase), so every tile's logits stay on chip between the two passes
   pl.npairs = p.B * pl.nkv;
@@ -601,12 +604,20 @@ int launch_inst(const CUtensorMap& mk, const CUtensorMap& mq, const TcArgs& a, i
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeCooperative;      // all CTAs co-resident: CTAs wait on each other's partials
-  attr[0].val.cooperative = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  int na = 0;
+  static const bool no_coop = getenv("FKV_NO_COOP") != nullptr;   // experiments only
+  if (!no_coop) {
+    attr[na].id = cudaLaunchAttributeCooperative;    // all CTAs co-resident: CTAs wait on each other's partials
+    attr[na].val.cooperative = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {                               // programmatic dependent launch: the prologue overlaps the previous kernel's tail
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;             // + programmatic dependent launch: the prologue overlaps the previous kernel's tail
+  cfg.numAttrs = na;
   FKV_CUDA_TRY(cudaLaunchKernelEx(&cfg, score_tc_kernel<W, G, kDef>, mk, mq, a));
   count_launch();
   return FKV_OK;
@@ -620,12 +631,14 @@ bool score_tensor_supported(const fkv_score_params& p) {
   return p.mode == FKV_MODE_GEMFILTER ? gemfilter_tensor_supported(p) : make_plan(p).ok;
 }
 
-int launch_score_tensor(const fkv_score_params& p, cudaStream_t s, bool with_hist) {
+int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
+  const bool with_hist = p.hist_slot >= 1 && p.hist_slot <= kHistSlots && p.mode != FKV_MODE_GEMFILTER &&
+                         p.B * (p.h1 - p.h0) <= kHistMaxRows;
   if (p.mode == FKV_MODE_GEMFILTER) return launch_score_gemfilter(p, s);
   const Plan pl = make_plan(p);
   if (!pl.ok) return FKV_EMODE;
   if (p.workspace_bytes < pl.part_bytes + FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
-  if (with_hist && p.B * (p.h1 - p.h0) > kHistMaxRows) return FKV_EINVAL;
+
   TcArgs a{};
   a.B = p.B; a.L = p.L; a.P = p.L - p.window_size; a.D = p.D;
   a.nkv = pl.nkv; a.kv0 = pl.kv0; a.n_tiles = pl.n_tiles; a.S = pl.S; a.half = pl.half; a.ks = p.kernel_size;
@@ -636,7 +649,7 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s, bool with_his
   char* ws = reinterpret_cast<char*>(p.workspace);
   a.sync_counter = reinterpret_cast<unsigned int*>(ws);
   a.part = reinterpret_cast<unsigned long long*>(ws + FKV_WORKSPACE_HEADER_BYTES);
-  void* hist = with_hist ? ws + kWsHistOffset : nullptr;
+  void* hist = with_hist ? ws + kWsHistOffset + (size_t)(p.hist_slot - 1) * kHistMaxRows * 4096 * 4 : nullptr;
   a.score = p.score; a.score_sb = p.score_stride_b; a.score_sh = p.score_stride_h; a.out_h0 = p.h0;
 
   CUtensorMap mk, mq;

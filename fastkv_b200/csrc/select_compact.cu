@@ -36,6 +36,7 @@ constexpr int kSpinLimit = 1 << 22;               // bounded spin: a broken barr
 
 // per-row control words in the persistent workspace region (zero between launches)
 enum { kCtlBarH = 0, kCtlBarS = 1, kCtlBarL = 2, kCtlCursor = 3, kCtlDepart = 4, kCtlWords = 8 };
+static_assert(kCtlWords * 4 == 32, "control block size is part of the workspace layout (common.cuh)");
 
 struct SelArgs {
   const float* score; int64_t stride_row;         // [rows][n], rows = B * Hsel
@@ -470,23 +471,22 @@ bool select_compact_supported(const fkv_topk_params& p, const fkv_gather_kv_para
   return row_chunks >= 8 && row_chunks <= 32;
 }
 
-size_t select_scratch_bytes(int rows) { return align_up((size_t)rows * kSelCand * sizeof(unsigned long long), 256); }
-
-// `workspace`: base of the call's workspace (persistent region in front); `scratch`: select_scratch_bytes(rows) bytes;
-// `have_hist`: the producer of the scores filled the rows' 12-bit histograms.
-int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& g, void* workspace, void* scratch,
-                          bool have_hist, cudaStream_t s) {
-  if (!workspace || !scratch || p.rows > kHistMaxRows) return FKV_EWORKSPACE;
+// `workspace`: base of the call's workspace (persistent region in front); `slot`: 1 or 2, the table set to use;
+// `have_hist`: the producer of the scores filled the slot's 12-bit histograms for these rows.
+int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& g, void* workspace, int slot,
+                          bool have_hist, cudaStream_t s, int max_ctas) {
+  if (!workspace || p.rows > kHistMaxRows || slot < 1 || slot > kHistSlots) return FKV_EWORKSPACE;
   char* wsb = static_cast<char*>(workspace);
+  const size_t row0 = (size_t)(slot - 1) * kHistMaxRows;
   const int es = dtype_size(g.dtype);
   SelArgs a{};
   a.score = p.src; a.stride_row = p.src_stride_row; a.n = p.n; a.k = p.k;
   a.idx_out = p.out; a.idx_stride_row = p.out_stride_row;
   a.have_hist = have_hist ? 1 : 0;
-  a.ctl = reinterpret_cast<uint32_t*>(wsb + kWsCtlOffset);
-  a.hist = reinterpret_cast<uint32_t*>(wsb + kWsHistOffset);
-  a.subhist = reinterpret_cast<uint32_t*>(wsb + kWsSubHistOffset);
-  a.list = reinterpret_cast<unsigned long long*>(scratch);
+  a.ctl = reinterpret_cast<uint32_t*>(wsb + kWsCtlOffset) + row0 * kCtlWords;
+  a.hist = reinterpret_cast<uint32_t*>(wsb + kWsHistOffset) + row0 * kMaxBins;
+  a.subhist = reinterpret_cast<uint32_t*>(wsb + kWsSubHistOffset) + row0 * kMaxBins;
+  a.list = reinterpret_cast<unsigned long long*>(wsb + kWsListOffset) + row0 * kSelCand;
   a.err = reinterpret_cast<uint32_t*>(wsb) + 5;
   a.kp = (const char*)g.k.ptr; a.vp = (const char*)g.v.ptr;
   a.ko = (char*)const_cast<void*>(g.k_out.ptr); a.vo = (char*)const_cast<void*>(g.v_out.ptr);
@@ -500,7 +500,8 @@ int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& 
   // CTAs per row: fill the chip once (the launch is cooperative: all CTAs must be co-resident), but leave every CTA at
   // least ~32 selected rows to rank and copy
   int R = 1;
-  const int sms = num_sms();
+  int sms = num_sms();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
   static const int env_r = getenv("FKV_SELECT_R") ? atoi(getenv("FKV_SELECT_R")) : 0;
   while (R < 32 && (long long)p.rows * (R * 2) <= sms && p.k / (R * 2) >= 32) R *= 2;
   if (env_r > 0) { R = 1; while (R * 2 <= env_r && R < 32 && (long long)p.rows * (R * 2) <= sms) R *= 2; }
@@ -523,7 +524,8 @@ int launch_select_compact(const fkv_topk_params& p, const fkv_gather_kv_params& 
   cfg.stream = s;
   cudaLaunchAttribute attr[2];
   int na = 0;
-  if (R > 1 && p.n > kSelCand) {                    // the R CTAs of a row wait for each other: they must be co-resident
+  static const bool no_coop = getenv("FKV_NO_COOP") != nullptr;   // experiments only
+  if (R > 1 && p.n > kSelCand && !no_coop) {        // the R CTAs of a row wait for each other: they must be co-resident
     attr[na].id = cudaLaunchAttributeCooperative;
     attr[na].val.cooperative = 1;
     ++na;

@@ -13,6 +13,47 @@ import torch
 from . import _lib as L
 
 
+class SelectOverlap:
+    """Runs the select + compact stage (K3 + K4) of ``compress`` call i on a side stream, so that it overlaps whatever
+    the caller's stream does next — in a prefill the layer's own attention and MLP, in bench.py the scoring kernel of
+    the next layer.  The compact K/V of a prefill are not read before the first decode step, so nothing on the
+    caller's stream has to wait for them until ``join()``.
+
+    The two histogram slots of the workspace (include/fastkv_b200.h) are used alternately: call i + 1 may score while
+    call i still selects; call i + 2 re-uses call i's slot and therefore waits for its select stage first.
+    Works eagerly and under CUDA-graph capture (fork / join through events)."""
+
+    SELECT_CTAS = 64                                   # measured on B200 (148 SMs): 84 scoring + 64 select CTAs is the best split
+
+    def __init__(self, device=None, partition: bool = False):
+        """``partition``: split the SMs between the scoring kernel on the caller's stream and the select + compact
+        kernel on the side stream (back-to-back update_kv calls, as in bench.py: both kernels are persistent and
+        latency-bound, so each loses little with fewer SMs and they truly run side by side).  Leave it off when other
+        work (attention, MLP) sits between the calls: the stage then simply fills SMs as they become free."""
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        sms = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.select_ctas = min(self.SELECT_CTAS, sms // 2) if partition else 0
+        self.score_ctas = sms - self.select_ctas if partition else 0
+        self.side = torch.cuda.Stream(self.device)
+        self.done = [None, None]
+        self.calls = 0
+        self._keep = []                                # buffers the side stream may still be using
+
+    def next_slot(self) -> int:
+        slot = (self.calls % 2) + 1
+        self.calls += 1
+        return slot
+
+    def join(self, stream=None):
+        """Make ``stream`` (default: current) wait for every select + compact stage issued so far."""
+        stream = torch.cuda.current_stream(self.device) if stream is None else stream
+        for i, ev in enumerate(self.done):
+            if ev is not None:
+                stream.wait_event(ev)
+                self.done[i] = None
+        self._keep.clear()
+
+
 def _score_params(mode, q, k, window_size, kernel_size, pooling, score, h0, h1, qh0, qh1, impl, ws):
     B, Hq, Lq, D = q.shape
     _, Hkv, Lk, Dk = k.shape
@@ -160,6 +201,63 @@ def gather_rows(hidden: torch.Tensor, idx: torch.Tensor, position_ids: Optional[
     return (out, pos_out) if position_ids is not None else out
 
 
+def _compress_overlapped(lib, ov, mode, q, k, v, W, kernel_size, pooling, capacity, h0, h1, impl, ws, score_buf, idx,
+                         k_out, v_out, tsp, imp, tsp_k):
+    """score on the current stream, select + compact on the side stream, TSP top-k on the current stream."""
+    dev = q.device
+    B, Hq, Lq, D = q.shape
+    Hkv = k.shape[1]
+    Hsel, P, n_sel = h1 - h0, Lq - W, capacity - W
+    main = torch.cuda.current_stream(dev)
+    slot = ov.next_slot()
+    if ov.done[slot - 1] is not None:                  # the call that used this slot's tables two calls ago
+        main.wait_event(ov.done[slot - 1])
+    sp = _score_params(mode, q, k, W, kernel_size, L.pool_code(pooling), score_buf, h0, h1, 0, 0, impl, ws)
+    sp.hist_slot = slot if P > 4096 else 0
+    sp.max_ctas = ov.score_ctas
+    have_hist = int(sp.hist_slot != 0 and lib.fkv_score_impl_name(C.byref(sp)) == b"tensor")
+    L.check(lib.fkv_score(C.byref(sp), main.cuda_stream))
+    fork = torch.cuda.Event()
+    fork.record(main)
+    ov.side.wait_event(fork)
+    sc = L.SelectCompactParams()
+    sc.struct_size = C.sizeof(L.SelectCompactParams)
+    sc.hist_slot, sc.have_hist = slot, have_hist
+    sc.score, sc.idx_out = score_buf.data_ptr(), idx.data_ptr()
+    g = sc.gather
+    g.struct_size = C.sizeof(L.GatherKvParams)
+    g.dtype, g.B, g.L, g.D = L.dtype_code(k.dtype), B, Lq, D
+    g.window_size, g.n_sel, g.h0, g.h1 = W, n_sel, h0, h1
+    g.head_div = Hq // Hkv if mode == L.MODE_SNAPKV else 1
+    g.k, g.v = L.view4(k), L.view4(v)
+    g.idx, g.idx_stride_b, g.idx_stride_h = idx.data_ptr(), idx.stride(0), idx.stride(1)
+    g.k_out, g.v_out = L.view4(k_out), L.view4(v_out)
+    sc.workspace, sc.workspace_bytes = ws.data_ptr(), ws.numel()
+    sc.max_ctas = ov.select_ctas
+    with torch.cuda.stream(ov.side):
+        L.check(lib.fkv_select_compact(C.byref(sc), ov.side.cuda_stream))
+        done = torch.cuda.Event()
+        done.record(ov.side)
+    ov.done[slot - 1] = done
+    if not torch.cuda.is_current_stream_capturing():
+        for t in (score_buf, idx, k_out, v_out, k, v):  # allocated on the caller's stream, used on the side stream
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(ov.side)
+    ov._keep.append(ws)
+    if tsp_k:
+        ws_ptr, ws_bytes = L.scratch(dev, lib.fkv_topk_workspace_bytes(B, P, tsp_k))
+        tp = L.TopkParams()
+        tp.struct_size = C.sizeof(L.TopkParams)
+        tp.rows, tp.n, tp.k, tp.order, tp.tail, tp.nsum = B, P, tsp_k, L.ORDER_INDEX_ASC, W, Hsel
+        tp.src, tp.src_stride_row, tp.src_stride_sum = score_buf.data_ptr(), score_buf.stride(0), score_buf.stride(1)
+        tp.out, tp.out_stride_row = tsp.data_ptr(), tsp.stride(0)
+        tp.imp_out = imp.data_ptr() if imp is not None else None
+        tp.workspace, tp.workspace_bytes = ws_ptr, ws_bytes
+        L.check(lib.fkv_topk(C.byref(tp), main.cuda_stream))
+        if imp is not None and Hsel == 1:
+            imp.copy_(score_buf[:, 0])
+
+
 def decode_attn(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, seq_len: int, *,
                 seq_len_dev: Optional[torch.Tensor] = None, scale: float = 0.0, num_splits: int = 0,
                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -205,11 +303,14 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
              pooling: str, capacity: int, tsp_len: int = 0, mode: int = L.MODE_FASTKV,
              head_range: Optional[Tuple[int, int]] = None, impl: int = L.IMPL_AUTO,
              k_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None,
-             return_aux: bool = False):
+             return_aux: bool = False, overlap: Optional[SelectOverlap] = None):
     """The fused update_kv chain: score -> per-head top-k -> KV compaction [-> TSP top-k].
 
     Returns (k_out [B,Hsel,C,D], v_out, tsp_idx [B,T] | None) and, with ``return_aux``, a dict with
-    the scores [B,Hsel,P], per-head indices [B,Hsel,C-W] and (TSP) importance [B,P]."""
+    the scores [B,Hsel,P], per-head indices [B,Hsel,C-W] and (TSP) importance [B,P].
+
+    ``overlap``: run the select + compact stage on the overlap object's side stream (k_out / v_out / idx are then
+    complete only after ``overlap.join()``); the scores and the TSP indices stay on the current stream."""
     L.require_cuda(q, k)
     L.require_cuda_or_pinned(v)
     lib = L.load()
@@ -234,6 +335,12 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
     tsp = torch.empty((B, tsp_len), dtype=torch.int64, device=dev) if tsp_k else None
     imp = torch.empty((B, P), dtype=torch.float32, device=dev) if (tsp_k and return_aux) else None
     ws = L.workspace(dev, lib.fkv_workspace_bytes(mode, B, Hq, Hkv, Lq, W, capacity, tsp_k))
+    if overlap is not None and v.is_cuda and B * Hsel <= L.SELECT_MAX_ROWS and 1 <= capacity - W <= 2048 and capacity - W <= P:
+        _compress_overlapped(lib, overlap, mode, q, k, v, W, kernel_size, pooling, capacity, h0, h1, impl, ws, score_buf, idx,
+                             k_out, v_out, tsp, imp, tsp_k)
+        if return_aux:
+            return k_out, v_out, tsp, dict(score=score_buf, idx=idx, importance=imp)
+        return k_out, v_out, tsp
     p = L.CompressParams()
     p.struct_size = C.sizeof(L.CompressParams)
     p.score = _score_params(mode, q, k, W, kernel_size, L.pool_code(pooling), score_buf, h0, h1, 0, 0, impl, ws)

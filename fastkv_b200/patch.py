@@ -274,7 +274,18 @@ def _make_forwards(mod, method, sliding_window_attr=False):
         hidden_states = inputs_embeds
         position_embeddings = self.rotary_emb(hidden_states, position_ids=position_ids)
         causal_mask, is_causal_kw = _prefill_mask(self.config, q_len, hidden_states, sliding_window_attr)
+        # prefill into the pre-allocated compact cache: the select + compact stage of every layer runs on a side stream
+        # under the layer's own attention / MLP (nothing reads the compact K/V before the first decode step)
+        overlap = None
+        if (q_len > 1 and method == "fastkv" and hidden_states.is_cuda and isinstance(past_key_values, CompactKVCache)
+                and getattr(self.config, "fastkv_overlap_select", True)):
+            overlap = getattr(self, "_fkv_overlap", None)
+            if overlap is None or overlap.device != hidden_states.device:
+                overlap = self._fkv_overlap = ops.SelectOverlap(hidden_states.device)
         for decoder_layer in self.layers[: self.config.num_hidden_layers]:
+            cluster = getattr(decoder_layer.self_attn, "kv_cluster", None)
+            if cluster is not None and hasattr(cluster, "overlap"):
+                cluster.overlap = overlap
             hidden_states = decoder_layer(
                 hidden_states, attention_mask=causal_mask, position_embeddings=position_embeddings,
                 position_ids=position_ids, past_key_values=past_key_values, use_cache=use_cache, **is_causal_kw, **kwargs)
@@ -285,6 +296,12 @@ def _make_forwards(mod, method, sliding_window_attr=False):
                 # the kept tokens stay in ascending order: still causal (and banded by INDEX, as the reference's
                 # flash-attn call is) over the shorter sequence
                 causal_mask, is_causal_kw = _prefill_mask(self.config, hidden_states.shape[1], hidden_states, sliding_window_attr)
+        if overlap is not None:
+            overlap.join()                            # the compact cache is complete when the prefill returns
+            for decoder_layer in self.layers[: self.config.num_hidden_layers]:
+                cluster = getattr(decoder_layer.self_attn, "kv_cluster", None)
+                if cluster is not None and hasattr(cluster, "overlap"):
+                    cluster.overlap = None
         hidden_states = self.norm(hidden_states)
         hidden_states = hidden_states[:, -1:, :]      # [FastKV] only the last token feeds lm_head
         return BaseModelOutputWithPast(last_hidden_state=hidden_states, past_key_values=past_key_values)

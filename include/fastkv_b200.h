@@ -25,12 +25,15 @@ extern "C" {
 
 /* Every `workspace` argument below is one kind of buffer: device memory, 256-byte aligned, passed ONCE through
  * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state owned by the library: 256 bytes
- * for the scoring kernel (launch epoch, departure counter, error word), 128 x 32 bytes of per-score-row barrier
- * counters and 2 x 128 score-row histograms of 4096 bins (first level filled by the scoring kernel, second level by
- * the select + compact kernel, which consumes both and leaves everything zeroed again).
+ * for the scoring kernel (launch epoch, departure counter, error word) and, for each of the two histogram SLOTS,
+ * FKV_SELECT_MAX_ROWS score rows' worth of barrier counters (32 bytes), first- and second-level 4096-bin histograms
+ * (filled by the scoring kernel / the select + compact kernel, which consumes both and leaves everything zeroed
+ * again) and candidate lists (4096 x 8 bytes).  Two slots let a caller run fkv_select_compact of call i on a side
+ * stream while fkv_score of call i+1 already fills the other slot.
  * Every entry point starts its own scratch PAST that region by itself, so one buffer can be shared by all calls
  * issued on a stream and no caller ever has to offset a pointer.  The *_workspace_bytes queries include it. */
-#define FKV_WORKSPACE_HEADER_BYTES (256 + 128 * 32 + 2 * 128 * 4096 * 4)
+#define FKV_SELECT_MAX_ROWS 64
+#define FKV_WORKSPACE_HEADER_BYTES (256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8)
 
 /* ---- enums ------------------------------------------------------------------------------- */
 enum { FKV_BF16 = 0, FKV_F16 = 1, FKV_F32 = 2 };                 /* element type of Q/K/V/hidden   */
@@ -86,6 +89,14 @@ typedef struct fkv_score_params {
   int64_t score_stride_b, score_stride_h;
   void* workspace;
   size_t workspace_bytes;
+  int32_t hist_slot;                /* 0: none.  1 or 2: additionally add the 12-bit histogram of every score written
+                                       to that slot's tables in the workspace, for a following fkv_select_compact with
+                                       the same slot (tensor-core path, B*(h1-h0) <= FKV_SELECT_MAX_ROWS; otherwise
+                                       the field is ignored and fkv_select_compact must be told hist_slot's tables
+                                       are empty through have_hist = 0) */
+  int32_t max_ctas;                 /* 0: use every SM.  > 0: cap the persistent grid of the tensor-core kernel, leaving
+                                       the other SMs to a kernel running concurrently on another stream (e.g. the
+                                       fkv_select_compact of the previous call)                                       */
 } fkv_score_params;
 
 int fkv_score(const fkv_score_params* p, void* stream);
@@ -135,6 +146,30 @@ typedef struct fkv_gather_kv_params {
 } fkv_gather_kv_params;
 
 int fkv_gather_kv(const fkv_gather_kv_params* p, void* stream);
+
+/* ---- K3 + K4 fused: per-head top-k with the KV compaction behind it, one launch ----------- */
+/*
+ * Replaces Tensor.topk + expand + 2x gather + 2x cat at baselines/fastkv/utils.py:113-121 (SnapKV twin
+ * snapkv/utils.py:88-101) in ONE kernel: for every selection head row of `score` ([B, h1-h0, P] dense fp32, P = L - W)
+ * the k = gather.n_sel best keys in (score desc, index asc) order go to idx_out [B, h1-h0, k] and their K / V rows +
+ * the W window rows to gather.k_out / v_out (same semantics as fkv_gather_kv; gather.idx is ignored).
+ * hist_slot (1 or 2) names the table set of the workspace to use; have_hist != 0 says fkv_score already filled that
+ * slot's histogram for exactly these rows (fkv_score_params.hist_slot), 0 makes the kernel build it itself.
+ * Limits: B*(h1-h0) <= FKV_SELECT_MAX_ROWS, k <= 2048 (FKV_EMODE otherwise: use fkv_topk + fkv_gather_kv).
+ * Calls that share a workspace AND a slot must be stream-ordered; different slots may overlap.
+ */
+typedef struct fkv_select_compact_params {
+  uint32_t struct_size;
+  int32_t hist_slot, have_hist;
+  const float* score;               /* [B, h1-h0, P] dense                                        */
+  int64_t* idx_out;                 /* [B, h1-h0, n_sel] dense                                    */
+  fkv_gather_kv_params gather;
+  void* workspace;
+  size_t workspace_bytes;
+  int32_t max_ctas;                 /* 0: use every SM.  > 0: cap the grid (see fkv_score_params.max_ctas)  */
+} fkv_select_compact_params;
+
+int fkv_select_compact(const fkv_select_compact_params* p, void* stream);
 
 /* ---- K4b: hidden-state / position-id propagation ---------------------------------------- */
 /*
@@ -202,7 +237,8 @@ int fkv_cache_append(const fkv_cache_append_params* p, void* stream);
  * (baselines/snapkv/utils.py:72-101) behind one call, for selection heads [h0,h1).
  * tsp_k > 0 additionally emits tsp_out[b, 0:tsp_k+W] (ascending) from the sum over the heads
  * computed by THIS call (single-GPU case; multi-GPU callers exchange `score` first and call
- * fkv_topk themselves).
+ * fkv_topk themselves).  score.hist_slot (0 = library's choice) selects the table set used between
+ * the scoring and the select + compact kernel.
  */
 typedef struct fkv_compress_params {
   uint32_t struct_size;
