@@ -147,7 +147,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_step_sample(ctx, cap, tsp_len, reps):
+def cpu_step_sample(ctx, cap, tsp_len, reps, warmup=1):
     """Times a bounded sample of the step on the CPU with the oracle port (same ATen op sequence as
     baselines/fastkv/utils.py:80-134, fp32): one ordinary full-context layer, the TSP layer with the
     hidden-state gather, and one post-TSP layer.  Returns (GB/s, seconds per sample, description)."""
@@ -173,7 +173,8 @@ def cpu_step_sample(ctx, cap, tsp_len, reps):
 
     nbytes = (layer_bytes(1, HKV, HQ, ctx, cap, 0) + layer_bytes(1, HKV, HQ, ctx, cap, tsp_len if ctx > tsp_len else 0)
               + layer_bytes(1, HKV, HQ, short, min(cap, short), 0))
-    sample()                                            # warm-up (allocator, thread pool)
+    for _ in range(max(1, warmup)):                     # warm-up (allocator, thread pool): untimed full samples
+        sample()
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -192,12 +193,16 @@ def run_reference(args):
     if rank != 0:
         return
     reps = max(1, args.steps)
-    for _ in range(max(0, args.warmup - 1)):
-        pass                                            # cpu_step_sample does its own warm-up call
-    gbs, sec, desc, cores = cpu_step_sample(args.ctx, args.capacity, args.tsp_len, reps)
+    gbs, sec, desc, cores = cpu_step_sample(args.ctx, args.capacity, args.tsp_len, reps, warmup=max(1, args.warmup))
+    # a "step" of this arm is the bounded 3-layer sample (its bytes / its time give the same GB/s metric); the time a
+    # full 32-layer step would take at that rate is reported separately
+    full_bytes = sum(layer_bytes(1, HKV, HQ, l, args.capacity, args.tsp_len if (t and l > args.tsp_len) else 0)
+                     for (l, t) in step_plan(args.ctx, args.capacity, args.tsp_len))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbs, 4), "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sec * 1e3, 3), "higher_is_better": True,
+        "steps": args.steps, "warmup": max(1, args.warmup), "ms_per_step": round(sec * 1e3, 3),
+        "ms_per_sample": round(sec * 1e3, 3), "ms_per_full_step_extrapolated": round(full_bytes / (gbs * 1e9) * 1e3, 1),
+        "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": round(gbs, 4), "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
@@ -205,6 +210,76 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def gpu_torch_baseline(ctx_list, cap, tsp_len, dev, peak):
+    """The reference's torch path (oracle port = the same ATen op chain as baselines/fastkv/utils.py:80-134) on CUDA
+    tensors of THIS box, bf16 and fp32: the like-for-like "reference on the same GPU" row (a reported baseline)."""
+    from oracle import fastkv_oracle as O
+    out = []
+    gen = torch.Generator(device=dev).manual_seed(7)
+    for ctx in ctx_list:
+        for dt in (torch.bfloat16, torch.float32):
+            try:
+                mk = lambda h: torch.randn(1, ctx, h, D, generator=gen, device=dev, dtype=torch.bfloat16).transpose(1, 2).to(dt)
+                q, k, v = mk(HQ), mk(HKV), mk(HKV)
+                knobs = dict(window_size=W, max_capacity_prompt=cap, kernel_size=KS, pooling=POOL, tsp_length=tsp_len, tsp_layer=False)
+                for _ in range(3):
+                    O.fastkv_update_kv(k, q, v, HQ // HKV, **knobs)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = 10
+                e0.record()
+                for _ in range(reps):
+                    O.fastkv_update_kv(k, q, v, HQ // HKV, **knobs)
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) * 1e3 / reps
+                nb = layer_bytes(1, HKV, HQ, ctx, cap, 0)
+                out.append({"ctx": ctx, "dtype": str(dt).replace("torch.", ""), "us_per_call": round(us, 1),
+                            "algorithmic_gbs": round(nb / us / 1e3, 1), "frac_of_peak": round(nb / us / 1e3 / peak, 4)})
+                del q, k, v
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                out.append({"ctx": ctx, "dtype": str(dt), "error": f"{type(e).__name__}: {e}"})
+    return {"what": "oracle port of FastKVCluster.update_kv (same ATen ops as the reference) on CUDA tensors, one non-TSP layer call, "
+                    "eager, CUDA events, 10 reps after 3 warm-ups", "rows": out}
+
+
+def decode_attention_numbers(dev, peak):
+    """K5 (split-K decode attention over the compact cache) at the two configured shapes: us per call and HBM GB/s
+    (algorithmic bytes 2 * B * Hkv * S * D * 2), CUDA-graph replay over rotating caches larger than L2."""
+    from fastkv_b200 import ops
+    rows = []
+    gen = torch.Generator(device=dev).manual_seed(11)
+    for (b, s, smax, what) in ((1, 2304, 2304, "configs[2]: C=2048 + 256 generated"), (8, 640, 768, "configs[3]: B=8, C=512 + 128 generated")):
+        nbuf = max(4, int(300e6 // (2 * b * HKV * smax * D * 2)) + 1)
+        caches = [(torch.randn(b, HKV, smax, D, generator=gen, device=dev, dtype=torch.bfloat16),
+                   torch.randn(b, HKV, smax, D, generator=gen, device=dev, dtype=torch.bfloat16)) for _ in range(nbuf)]
+        q = torch.randn(b, HQ, D, generator=gen, device=dev, dtype=torch.bfloat16)
+        out = torch.empty_like(q)
+        for kc, vc in caches[:2]:
+            ops.decode_attn(q, kc, vc, s, out=out)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for kc, vc in caches:
+                ops.decode_attn(q, kc, vc, s, out=out)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / (5 * nbuf)
+        nb = 2 * b * HKV * s * D * 2
+        rows.append({"batch": b, "seq_len": s, "config": what, "us_per_call": round(us, 2), "algorithmic_bytes": nb,
+                     "gbs": round(nb / us / 1e3, 1), "frac_of_peak": round(nb / us / 1e3 / peak, 4), "caches_rotated": nbuf})
+        del caches
+        torch.cuda.empty_cache()
+    return rows
 
 
 def workload_config(args, n):
@@ -293,7 +368,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- value: device-resident inputs, graph replay of the whole step --------------------------
-    for _ in range(max(args.warmup, 3)):
+    args.warmup = max(args.warmup, 3)                   # the timing rules need >= 3 warm-up steps; the line reports what ran
+    for _ in range(args.warmup):
         one_step()
     torch.cuda.synchronize()
     c0 = lib.fkv_launch_count()
@@ -498,6 +574,18 @@ def run_ours(args):
                "ms_per_step": round(dt.item() / e_steps * 1e3, 3), "steps": e_steps,
                "api": "FastKVCluster.update_kv(key_states, query_states, value_states, ...) on pinned host tensors"}
 
+    # ---- the reference's torch path on this GPU + K5 numbers (rank 0, N == 1 only) ------------------
+    gpu_torch = k5 = None
+    if rank == 0 and world == 1 and not args.no_sweep:
+        try:
+            gpu_torch = gpu_torch_baseline((32768, 131072), cap, tsp_len, dev, peak)
+        except Exception as e:  # noqa: BLE001
+            gpu_torch = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            k5 = decode_attention_numbers(dev, peak)
+        except Exception as e:  # noqa: BLE001
+            k5 = {"error": f"{type(e).__name__}: {e}"}
+
     # ---- cpu baseline (rank 0, N == 1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -529,14 +617,15 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, n_prompts),
             "algorithmic_bytes_per_step": int(total_bytes_step),
             "timed_with": timed_with + ("" if args.no_overlap else "; select + compact stage of layer i on a side stream (joined at step end)"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps),
             "launches_per_step": int(launches_per_step),
-            "roofline": roofline, "cpu_baseline": cpu, "context_sweep": context_sweep, "model": model_extras,
+            "roofline": roofline, "cpu_baseline": cpu, "gpu_torch_baseline": gpu_torch, "decode_attention": k5,
+            "context_sweep": context_sweep, "model": model_extras,
         }
         print(json.dumps(line))
     if world > 1:

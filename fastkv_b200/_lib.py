@@ -243,7 +243,7 @@ def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 
 SELECT_MAX_ROWS = 64
-WS_HEADER = 256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8   # FKV_WORKSPACE_HEADER_BYTES: the library's persistent region
+WS_HEADER = 256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8 + 4096   # FKV_WORKSPACE_HEADER_BYTES: the library's persistent region
 
 
 def scratch(device: torch.device, nbytes: int):

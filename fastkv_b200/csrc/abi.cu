@@ -297,11 +297,11 @@ int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream) {
     return FKV_EALIGN;
   if (!aligned16(p->q) || !aligned16(p->out)) return FKV_EALIGN;
   if (p->seq_len_dev && p->max_seq_len < 1) return FKV_EINVAL;      // the device-side length needs its bound
-  fkv_decode_attn_params q = *p;                       // scratch starts past the scoring header
-  if (!q.workspace || q.workspace_bytes < FKV_WORKSPACE_HEADER_BYTES) return FKV_EWORKSPACE;
-  q.workspace = static_cast<char*>(q.workspace) + FKV_WORKSPACE_HEADER_BYTES;
-  q.workspace_bytes -= FKV_WORKSPACE_HEADER_BYTES;
-  return launch_decode_attn(q, (cudaStream_t)stream);
+  // the kernel keeps its arrival tickets in the persistent region: the workspace must be an initialised one
+  if (!p->workspace || p->workspace_bytes < FKV_WORKSPACE_HEADER_BYTES ||
+      !workspace_registered(p->workspace, FKV_WORKSPACE_HEADER_BYTES))
+    return FKV_EWORKSPACE;
+  return launch_decode_attn(*p, (cudaStream_t)stream);
 }
 
 int fkv_cache_append(const fkv_cache_append_params* p, void* stream) {

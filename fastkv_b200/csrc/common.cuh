@@ -42,7 +42,9 @@ constexpr size_t kWsCtlOffset = 256;                               // u32[rows][
 constexpr size_t kWsHistOffset = kWsCtlOffset + kHistTotalRows * 32;                      // u32[rows][4096]: 12-bit histogram of a score row
 constexpr size_t kWsSubHistOffset = kWsHistOffset + (size_t)kHistTotalRows * 4096 * 4;    // same, second level (threshold bin)
 constexpr size_t kWsListOffset = kWsSubHistOffset + (size_t)kHistTotalRows * 4096 * 4;    // u64[rows][4096]: candidate lists
-static_assert(kWsListOffset + (size_t)kHistTotalRows * 4096 * 8 == FKV_WORKSPACE_HEADER_BYTES, "workspace header layout");
+constexpr size_t kWsTicketOffset = kWsListOffset + (size_t)kHistTotalRows * 4096 * 8;     // u32[1024]: decode-attention arrival tickets
+constexpr size_t kWsTickets = 1024;
+static_assert(kWsTicketOffset + kWsTickets * 4 == FKV_WORKSPACE_HEADER_BYTES, "workspace header layout");
 
 constexpr uint32_t kWorkspaceMagic = 0xF457CB20u;   // written at byte 16 of a workspace by fkv_workspace_init
 

@@ -28,12 +28,12 @@ extern "C" {
  * for the scoring kernel (launch epoch, departure counter, error word) and, for each of the two histogram SLOTS,
  * FKV_SELECT_MAX_ROWS score rows' worth of barrier counters (32 bytes), first- and second-level 4096-bin histograms
  * (filled by the scoring kernel / the select + compact kernel, which consumes both and leaves everything zeroed
- * again) and candidate lists (4096 x 8 bytes).  Two slots let a caller run fkv_select_compact of call i on a side
+ * again) and candidate lists (4096 x 8 bytes); finally 1024 arrival tickets of the decode-attention kernel.  Two slots let a caller run fkv_select_compact of call i on a side
  * stream while fkv_score of call i+1 already fills the other slot.
  * Every entry point starts its own scratch PAST that region by itself, so one buffer can be shared by all calls
  * issued on a stream and no caller ever has to offset a pointer.  The *_workspace_bytes queries include it. */
 #define FKV_SELECT_MAX_ROWS 64
-#define FKV_WORKSPACE_HEADER_BYTES (256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8)
+#define FKV_WORKSPACE_HEADER_BYTES (256 + 128 * 32 + 2 * 128 * 4096 * 4 + 128 * 4096 * 8 + 4096)
 
 /* ---- enums ------------------------------------------------------------------------------- */
 enum { FKV_BF16 = 0, FKV_F16 = 1, FKV_F32 = 2 };                 /* element type of Q/K/V/hidden   */

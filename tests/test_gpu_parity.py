@@ -529,6 +529,49 @@ def test_decode_attention_vs_oracle(dtype, tol, b, hq, hkv, d, s, smax):
     assert torch.equal(out, out2)
 
 
+@pytest.mark.parametrize("b,hq,hkv,d,s,smax", [(1, 32, 8, 128, 2304, 2304), (8, 32, 8, 128, 640, 768), (2, 24, 8, 128, 333, 512),
+                                               (1, 32, 32, 64, 100, 128)])
+def test_decode_attention_vs_library_attention_on_the_gpu(b, hq, hkv, d, s, smax):
+    """the reference's decode attention is flash-attn's kernel (third party, unpinned).  Cross-check K5 on
+    the GPU box against torch SDPA (always) and the installed flash_attn (when it runs on this GPU), bf16 tolerance."""
+    import torch.nn.functional as F
+    from fastkv_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(s)
+    q = torch.randn(b, hq, d, generator=g, device=DEV, dtype=torch.bfloat16)
+    kc = torch.randn(b, hkv, smax, d, generator=g, device=DEV, dtype=torch.bfloat16)
+    vc = torch.randn(b, hkv, smax, d, generator=g, device=DEV, dtype=torch.bfloat16)
+    got = ops.decode_attn(q, kc, vc, s).float()
+    ke = kc[:, :, :s].repeat_interleave(hq // hkv, dim=1)
+    ve = vc[:, :, :s].repeat_interleave(hq // hkv, dim=1)
+    sdpa = F.scaled_dot_product_attention(q[:, :, None, :], ke, ve, is_causal=False)[:, :, 0].float()
+    assert torch.allclose(got, sdpa, atol=2e-2, rtol=2e-2), (got - sdpa).abs().max().item()
+    try:
+        from flash_attn import flash_attn_func
+        fa = flash_attn_func(q[:, None], kc[:, :, :s].transpose(1, 2), vc[:, :, :s].transpose(1, 2), causal=True)[:, 0].float()
+    except Exception as e:  # noqa: BLE001  (flash-attn 2.x has no sm_100 kernels on some builds)
+        pytest.skip(f"SDPA leg passed; flash_attn not runnable here: {type(e).__name__}: {str(e)[:80]}")
+    assert torch.allclose(got, fa, atol=2e-2, rtol=2e-2), (got - fa).abs().max().item()
+
+
+def test_full_cache_drops_the_row_and_keeps_the_length():
+    """Device-resident lengths (CUDA-graph decode): appending to a full cache must not advance the length, and the
+    attention kernel never reads past max_seq_len."""
+    from fastkv_b200 import ops
+    b, hkv, d, smax = 1, 2, 128, 16
+    kc = torch.randn(b, hkv, smax, d, device=DEV, dtype=torch.bfloat16)
+    vc = torch.randn(b, hkv, smax, d, device=DEV, dtype=torch.bfloat16)
+    k0, v0 = kc.clone(), vc.clone()
+    sl = torch.tensor([smax], dtype=torch.int32, device=DEV)
+    kn = torch.randn(b, hkv, 1, d, device=DEV, dtype=torch.bfloat16)
+    ops.cache_append(kn, kn, kc, vc, 0, seq_len_dev=sl, bump=True)
+    assert sl.item() == smax and torch.equal(kc, k0) and torch.equal(vc, v0)
+    q = torch.randn(b, 8, d, device=DEV, dtype=torch.bfloat16)
+    sl.fill_(smax + 5)                                  # a corrupted length is clamped, not followed
+    got = ops.decode_attn(q, kc, vc, 0, seq_len_dev=sl)
+    exp = O.decode_attention(q.cpu(), kc.cpu(), vc.cpu(), smax)
+    assert torch.allclose(got.cpu().float(), exp, atol=2e-2, rtol=2e-2)
+
+
 def test_cache_append_and_decode_loop():
     from fastkv_b200 import ops
     g = torch.Generator().manual_seed(9)
