@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--capacity", type=int, default=2048)
     ap.add_argument("--tsp-len", type=int, default=2048)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = N prompts, Hkv/N heads of each per rank (default); strong = ONE prompt, Hkv/N heads per rank")
     ap.add_argument("--no-overlap", action="store_true", help="run the select + compact stage on the same stream as the scoring")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -282,6 +284,22 @@ def decode_attention_numbers(dev, peak):
     return rows
 
 
+def _try_full_graph(step):
+    """Capture the whole multi-GPU step (NCCL all-gather included) as one CUDA graph; None when that fails."""
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        g.replay()
+        torch.cuda.synchronize()
+        _try_full_graph.graph = g
+        return g
+    except Exception as e:  # noqa: BLE001
+        print(f"[bench] capturing the NCCL exchange failed ({type(e).__name__}: {e}); using two graphs around an eager TSP layer", file=sys.stderr)
+        torch.cuda.synchronize()
+        return None
+
+
 def workload_config(args, n):
     return {
         "workload": (f"BASELINE configs[1]: Llama-3.1-8B-shaped layer tensors (32 q / 8 kv heads, d=128, hidden 4096), "
@@ -289,7 +307,7 @@ def workload_config(args, n):
                      f"{args.capacity}, window {W}, kernel {KS} {POOL}; step = the 32 update_kv calls of one prefill "
                      f"(+ hidden-state gather at the TSP layer)"),
         "ctx": args.ctx, "capacity": args.capacity, "tsp_len": args.tsp_len, "window": W, "kernel_size": KS,
-        "pooling": POOL, "prompts": n, "sharding": f"kv-heads/{n}" if n > 1 else "none",
+        "pooling": POOL, "prompts": n, "sharding": f"kv-heads/{int(os.environ.get('WORLD_SIZE', '1'))}" if int(os.environ.get('WORLD_SIZE', '1')) > 1 else "none",
         "l2": "per-layer distinct K/V/Q buffers: each step streams > 2 GB, far above the 126 MB L2",
     }
 
@@ -315,7 +333,8 @@ def run_ours(args):
     lib = L.load()
     impl = {"auto": L.IMPL_AUTO, "simple": L.IMPL_SIMPLE, "tensor": L.IMPL_TENSOR}[args.score_impl]
 
-    n_prompts = world                                   # weak scaling: one prompt per GPU in the batch
+    strong = args.scaling == "strong" and world > 1
+    n_prompts = 1 if strong else world                  # weak scaling: one prompt per GPU in the batch
     hkv_local, hq_local = HKV // world, HQ // world
     ctx, cap, tsp_len = args.ctx, args.capacity, args.tsp_len
     plan = step_plan(ctx, cap, tsp_len)
@@ -334,7 +353,11 @@ def run_ours(args):
         cl.score_impl = impl
         cl.shard = shard
         layers.append((cl, q, k, v))
-    hidden = torch.randn(n_prompts, ctx, HIDDEN, generator=gen, device=dev, dtype=torch.bfloat16)
+    # hidden states: every prompt's rows are propagated by exactly ONE rank (weak: rank r owns prompt r; strong: the
+    # single prompt's hidden columns are split over the ranks), so no propagated byte is moved or counted twice
+    own_prompt = rank if (world > 1 and not strong) else 0
+    hid_cols = HIDDEN // world if strong else HIDDEN
+    hidden = torch.randn(1, ctx, hid_cols, generator=gen, device=dev, dtype=torch.bfloat16)
     pos = torch.arange(ctx, device=dev).unsqueeze(0)
 
     # the select + compact stage of layer i runs on a side stream, overlapping the scoring of layer i + 1 (in a model:
@@ -348,7 +371,7 @@ def run_ours(args):
         for (cl, q, k, v) in sel:
             ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
             if tsp is not None:
-                out = ops.gather_rows(hidden, tsp, pos)
+                out = ops.gather_rows(hidden, tsp[own_prompt:own_prompt + 1], pos)
         if overlap is not None:
             overlap.join()
         return out
@@ -356,11 +379,10 @@ def run_ours(args):
     def one_step():
         return run_layers(layers)
 
-    bytes_step = 0
+    # algorithmic bytes of the whole job = those of n_prompts single-GPU prefills (nothing replicated is counted)
+    total_bytes_step = 0
     for (l, is_tsp) in plan:
-        c_eff = cap
-        bytes_step += layer_bytes(n_prompts, hkv_local, hq_local, l, c_eff, tsp_len if (is_tsp and l > tsp_len) else 0)
-    total_bytes_step = bytes_step * world
+        total_bytes_step += layer_bytes(n_prompts, HKV, HQ, l, cap, tsp_len if (is_tsp and l > tsp_len) else 0)
 
     def barrier():
         if world > 1:
@@ -391,6 +413,10 @@ def run_ours(args):
                 torch.cuda.synchronize()
                 run = graph.replay
                 timed_with = "cuda-graph replay of the C-ABI launches"
+            elif os.environ.get("FKV_BENCH_NCCL_IN_GRAPH", "0") == "1" and _try_full_graph(one_step) is not None:
+                graph = _try_full_graph.graph
+                run = graph.replay
+                timed_with = "cuda-graph replay of the whole step, the TSP layer's NCCL exchange captured in the graph"
             else:
                 tsp_pos = [i for i, (l, t) in enumerate(plan) if t][0]
                 pre, mid, post = layers[:tsp_pos], layers[tsp_pos:tsp_pos + 1], layers[tsp_pos + 1:]
@@ -545,8 +571,8 @@ def run_ours(args):
             h2d += n_prompts * (hkv_local * l * D + hq_local * W * D + hkv_local * min(cap, l) * D) * es
             d2h += 2 * n_prompts * hkv_local * min(cap, l) * D * es
             if is_tsp and l > tsp_len:
-                h2d += n_prompts * tsp_len * (8 + HIDDEN * es)       # index set + the T gathered hidden rows
-                d2h += n_prompts * tsp_len * (8 + 8 + HIDDEN * es)
+                h2d += n_prompts * tsp_len * 8 + tsp_len * hid_cols * es       # index set + the T gathered hidden rows of the own prompt / column shard
+                d2h += n_prompts * tsp_len * 8 + tsp_len * (8 + hid_cols * es)
 
         def host_step():
             res = None
@@ -554,7 +580,7 @@ def run_ours(args):
                 ko, vo, tsp = cl.update_kv(k, q, v, None, HQ // HKV, 0)
                 if tsp is not None:
                     # hidden states stay in pinned host memory: only the T selected rows cross the bus
-                    nh, npos = ops.gather_rows(hidden_host, tsp.to(dev, non_blocking=True), pos)
+                    nh, npos = ops.gather_rows(hidden_host, tsp[own_prompt:own_prompt + 1].to(dev, non_blocking=True), pos)
                     res = (nh.cpu(), npos.cpu())
             return res
 
@@ -618,7 +644,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": workload_config(args, n_prompts),
             "algorithmic_bytes_per_step": int(total_bytes_step),
             "timed_with": timed_with + ("" if args.no_overlap else "; select + compact stage of layer i on a side stream (joined at step end)"),
@@ -629,6 +655,11 @@ def run_ours(args):
         }
         print(json.dumps(line))
     if world > 1:
+        graph = sgraph = None                           # graphs holding NCCL work go before the communicator
+        if hasattr(_try_full_graph, "graph"):
+            del _try_full_graph.graph
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
 
 

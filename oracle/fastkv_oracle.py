@@ -19,7 +19,8 @@ classes from ``/root/reference`` and stores their outputs; ``tests/test_oracle_g
 this restatement against those stored outputs bit-for-bit (the restatement issues the same ATen
 ops in the same order, so on the same torch build the results are identical, ties included).
 
-All functions take torch CPU tensors.  ``compute_dtype`` mirrors the reference's behaviour of
+All functions take torch CPU tensors (the same code also runs on CUDA tensors: bench.py times it there as the
+"reference torch path on this GPU" baseline).  ``compute_dtype`` mirrors the reference's behaviour of
 working in the dtype of the incoming tensors (fp32 under the parity protocol of SURVEY.md §8c).
 """
 from __future__ import annotations
@@ -45,12 +46,12 @@ def expand_kv_heads(x: torch.Tensor, groups: int) -> torch.Tensor:
     return x.unsqueeze(2).expand(b, h, groups, l, d).reshape(b, h * groups, l, d)
 
 
-def window_causal_bias(window: int, dtype: torch.dtype) -> torch.Tensor:
+def window_causal_bias(window: int, dtype: torch.dtype, device=None) -> torch.Tensor:
     """[W,W] additive bias: 0 where col <= row, finfo(dtype).min elsewhere.
 
     Follows baselines/fastkv/utils.py:95-99."""
-    bias = torch.full((window, window), torch.finfo(dtype).min, dtype=dtype)
-    cols = torch.arange(window)
+    bias = torch.full((window, window), torch.finfo(dtype).min, dtype=dtype, device=device)
+    cols = torch.arange(window, device=device)
     bias.masked_fill_(cols[None, :] <= cols[:, None], 0)
     return bias
 
@@ -103,7 +104,7 @@ def window_votes(q: torch.Tensor, k_expanded: torch.Tensor, window: int) -> torc
     window); the returned votes drop the last W key columns."""
     d = q.shape[-1]
     logits = torch.matmul(q[..., -window:, :], k_expanded.transpose(2, 3)) / math.sqrt(d)
-    logits[:, :, -window:, -window:] += window_causal_bias(window, logits.dtype)[None, None]
+    logits[:, :, -window:, -window:] += window_causal_bias(window, logits.dtype, logits.device)[None, None]
     probs = F.softmax(logits, dim=-1, dtype=torch.float32).to(q.dtype)
     return probs[:, :, -window:, :-window].sum(dim=-2)
 
@@ -160,7 +161,7 @@ def fastkv_update_kv(
     if tsp_layer and q_len > t_len:                                          # :126 (strict >)
         tr.importance = tr.score.sum(dim=-2)                                 # :127
         picked = select(tr.importance, t_len - w)
-        tail = torch.arange(q_len - w, q_len).unsqueeze(0).repeat(bsz, 1)    # :128
+        tail = torch.arange(q_len - w, q_len, device=key_states.device).unsqueeze(0).repeat(bsz, 1)    # :128
         tr.tsp_idx = torch.sort(torch.cat([picked, tail], dim=-1), dim=1).values   # :129-130
     return tr
 
