@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-sweep", action="store_true", help="skip the 32k / 128k single-call extra")
     ap.add_argument("--no-model", action="store_true")
     ap.add_argument("--score-impl", default="auto", choices=["auto", "simple", "tensor"])
+    ap.add_argument("--sweep", default="", metavar="FILE.md",
+                    help="instead of the bench line: run the config-5 kernel sweep (ours vs the reference torch path on this GPU) and write a table")
     return ap.parse_args()
 
 
@@ -663,8 +665,65 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sweep(args):
+    """BASELINE configs[4]: kernel sweep over context x budget x window / kernel / pooling x selection mode, every row next
+    to the reference's torch path (oracle port, same ATen ops) timed on THIS GPU in bf16."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sweep as S
+    from oracle import fastkv_oracle as O
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+
+    def torch_us(c):
+        g = torch.Generator(device=dev).manual_seed(1)
+        mk = lambda h: torch.randn(c["b"], c["l"], h, D, generator=g, device=dev, dtype=torch.bfloat16).transpose(1, 2)
+        q, k, v = mk(HQ), mk(HKV), mk(HKV)
+        if c["mode"] == "fastkv":
+            fn = lambda: O.fastkv_update_kv(k, q, v, HQ // HKV, window_size=c["w"], max_capacity_prompt=c["c"], kernel_size=c["ks"],
+                                            pooling=c["pool"], tsp_layer=False)
+        elif c["mode"] == "snapkv":
+            fn = lambda: O.snapkv_update_kv(O.expand_kv_heads(k, HQ // HKV), q, O.expand_kv_heads(v, HQ // HKV), window_size=c["w"],
+                                            max_capacity_prompt=c["c"], kernel_size=c["ks"], pooling=c["pool"])
+        else:
+            fn = lambda: O.gemfilter_select(q[:1], k[:1], HQ // HKV, c["c"])
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e3 / 5
+
+    rows = [f"| mode | B | L | C | W | kernel | pool | ours: pipeline µs | ours: score stage µs | reference torch on this GPU µs (bf16, eager) | speed-up | "
+            f"algorithmic MB | ours GB/s | frac of {peak:.0f} GB/s |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    for c in S.grid(quick=False):
+        tot, sc = S.run_one(**c)
+        try:
+            ref = torch_us(c)
+        except Exception as e:  # noqa: BLE001
+            ref = float("nan")
+            print(f"[sweep] torch path failed for {c}: {type(e).__name__}: {e}", file=sys.stderr)
+        torch.cuda.empty_cache()
+        nb = S.alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"])
+        gbs = nb / tot / 1e3
+        rows.append(f"| {c['mode']} | {c['b']} | {c['l']} | {c['c']} | {c['w']} | {c['ks']} | {c['pool']} | {tot:.1f} | {sc:.1f} | {ref:.0f} | "
+                    f"{ref / tot:.1f}x | {nb / 1e6:.1f} | {gbs:.0f} | {gbs / peak:.2f} |")
+        print(rows[-1], flush=True)
+    os.makedirs(os.path.dirname(args.sweep) or ".", exist_ok=True)
+    with open(args.sweep, "w") as f:
+        f.write("\n".join(rows) + "\n")
+
+
 def main():
     args = parse()
+    if args.sweep:
+        run_sweep(args)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

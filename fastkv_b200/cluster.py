@@ -101,13 +101,13 @@ class FastKVCluster:
         if key_states.shape[1] * num_key_value_groups != num_heads:
             raise ValueError("fastkv_b200: num_key_value_groups does not match the head counts")
 
+        k_dst = v_dst = None
+        if self.out_provider is not None and not host_io:
+            k_dst, v_dst = self.out_provider(bsz, key_states.shape[1], self.max_capacity_prompt, head_dim,
+                                             key_states.dtype, key_states.device)
         if self.shard is not None and self.shard.world_size > 1 and want_tsp:
-            k, v, tsp = self._update_kv_sharded(key_states, query_states, value_states)
+            k, v, tsp = self._update_kv_sharded(key_states, query_states, value_states, k_dst, v_dst)
         else:
-            k_dst = v_dst = None
-            if self.out_provider is not None and not host_io:
-                k_dst, v_dst = self.out_provider(bsz, key_states.shape[1], self.max_capacity_prompt, head_dim,
-                                                 key_states.dtype, key_states.device)
             res = ops.compress(query_states, key_states, value_states, window_size=self.window_size,
                                kernel_size=self.kernel_size, pooling=self.pooling,
                                capacity=self.max_capacity_prompt, tsp_len=self.tsp_length if want_tsp else 0,
@@ -122,13 +122,14 @@ class FastKVCluster:
             torch.cuda.current_stream().synchronize()      # results are on the host when we return
         return k, v, tsp
 
-    def _update_kv_sharded(self, key_states, query_states, value_states):
+    def _update_kv_sharded(self, key_states, query_states, value_states, k_dst=None, v_dst=None):
         """KV-head-sharded TSP layer: local compress, exchange per-head scores, identical global top-k."""
         w = self.window_size
         k, v, _, aux = ops.compress(query_states, key_states, value_states, window_size=w,
                                     kernel_size=self.kernel_size, pooling=self.pooling,
                                     capacity=self.max_capacity_prompt, tsp_len=0, mode=L.MODE_FASTKV,
-                                    impl=self.score_impl, return_aux=True, overlap=self.overlap)
+                                    impl=self.score_impl, return_aux=True, overlap=self.overlap,
+                                    k_out=k_dst, v_out=v_dst)
         tsp, imp = self.shard.global_tsp(aux["score"], self.tsp_length - w, w)
         if self.keep_aux:
             aux["importance"] = imp

@@ -17,17 +17,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 
-def build_model(kind, layers=None, dtype=torch.bfloat16, device="cuda"):
+def build_model(kind, layers=None, dtype=torch.bfloat16, device="cuda", tp=1):
+    """``tp`` > 1: this rank's tensor-parallel SHARD of the model (heads and MLP columns divided by tp; the all-reduces
+    behind o_proj / down_proj are added by ``add_tp_allreduce``).  The KV heads a rank owns are exactly the heads its
+    FastKV compressor scores, selects and compacts."""
     from transformers import LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM
     if kind == "llama":       # Llama-3.1-8B-Instruct public model-card shape (SURVEY.md §8)
-        cfg = LlamaConfig(hidden_size=4096, intermediate_size=14336, num_hidden_layers=layers or 32, num_attention_heads=32,
-                          num_key_value_heads=8, head_dim=128, vocab_size=128256, max_position_embeddings=131072,
+        cfg = LlamaConfig(hidden_size=4096, intermediate_size=14336 // tp, num_hidden_layers=layers or 32, num_attention_heads=32 // tp,
+                          num_key_value_heads=8 // tp, head_dim=128, vocab_size=128256, max_position_embeddings=131072,
                           rope_theta=500000.0, attn_implementation="sdpa")
         cls = LlamaForCausalLM
-    else:                     # Ministral-8B-Instruct-2410 shape
-        cfg = MistralConfig(hidden_size=4096, intermediate_size=12288, num_hidden_layers=layers or 36, num_attention_heads=32,
-                            num_key_value_heads=8, head_dim=128, vocab_size=131072, max_position_embeddings=131072,
-                            sliding_window=None, attn_implementation="sdpa")
+    else:                     # Ministral-8B-Instruct-2410 shape (sliding_window 32768: a no-op up to 32k prompts)
+        cfg = MistralConfig(hidden_size=4096, intermediate_size=12288 // tp, num_hidden_layers=layers or 36, num_attention_heads=32 // tp,
+                            num_key_value_heads=8 // tp, head_dim=128, vocab_size=131072, max_position_embeddings=131072,
+                            sliding_window=32768, attn_implementation="sdpa")
         cls = MistralForCausalLM
     torch.manual_seed(0)
     with torch.device(device):
@@ -37,6 +40,20 @@ def build_model(kind, layers=None, dtype=torch.bfloat16, device="cuda"):
     return model.eval()
 
 
+def add_tp_allreduce(model):
+    """Row-parallel projections: sum the partial outputs of o_proj and down_proj over the ranks (2 all-reduces per
+    layer, library NCCL; outside the hot path).  Embedding, norms and lm_head are replicated."""
+    import torch.distributed as dist
+
+    def hook(_mod, _inp, out):
+        dist.all_reduce(out)
+        return out
+
+    for layer in model.model.layers:
+        layer.self_attn.o_proj.register_forward_hook(hook)
+        layer.mlp.down_proj.register_forward_hook(hook)
+
+
 def run(args):
     from fastkv_b200 import patch
     tsp_idx = args.tsp_idx if args.tsp_idx >= 0 else (15 if args.model == "llama" else 17)
@@ -44,11 +61,25 @@ def run(args):
         patch.replace_llama(args.method)
     else:
         patch.replace_mistral(args.method)
-    model = build_model(args.model, layers=args.layers)
+    tp = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if tp > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
+    model = build_model(args.model, layers=args.layers, tp=tp)
+    if tp > 1:
+        add_tp_allreduce(model)
     a = types.SimpleNamespace(method=args.method, max_capacity_prompts=args.capacity, window_size=8, kernel_size=7,
                               pooling="avgpool", retain_rate=0.1, eviction_mode="constant", tsp_len=args.tsp_len,
                               tsp_rate=0.2, tsp_idx=tsp_idx, merge=None)
     patch.set_model(model, a)
+    if tp > 1 and args.method == "fastkv":
+        from fastkv_b200.dist import HeadShard
+        shard = HeadShard(exchange="gather")          # the path's one exchange: per-head scores at the TSP layer
+        for layer in model.model.layers:
+            layer.self_attn.kv_cluster.shard = shard
     ids = torch.ones((args.batch, args.ctx), dtype=torch.int64, device="cuda")      # benchmark/e2e.py:55
     model.config.fastkv_max_new_tokens = args.genlen
     model.model.config.fastkv_max_new_tokens = args.genlen
@@ -65,7 +96,7 @@ def run(args):
             cache = out.past_key_values
             tok = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
             s2, e2 = ev(), ev()
-            if args.graph and args.method != "fullkv":
+            if args.graph and args.method != "fullkv" and tp == 1:   # (NCCL all-reduces inside a captured graph hang on this stack)
                 gd = patch.GraphedDecode(model, cache, tok)          # 2 eager steps + capture (untimed)
                 n_timed = args.genlen - 1 - 2
                 s2.record()
@@ -86,15 +117,27 @@ def run(args):
             del out, cache
     ttft = sum(r[0] for r in results) / len(results)
     dec = sum(r[1] for r in results) / len(results)
+    if tp > 1:                                        # max over ranks, like bench.py
+        import torch.distributed as dist
+        t = torch.tensor([ttft, dec], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ttft, dec = t[0].item(), t[1].item()
     line = {
+        "n_gpus": tp, "parallelism": f"tp{tp} (kv-head-sharded compressor, 2 hidden all-reduces per layer)" if tp > 1 else "none",
         "model": args.model, "layers": args.layers or (32 if args.model == "llama" else 36), "method": args.method,
         "ctx": args.ctx, "batch": args.batch, "capacity": args.capacity, "tsp_len": args.tsp_len, "tsp_idx": tsp_idx,
-        "genlen": args.genlen, "decode_cuda_graph": bool(args.graph and args.method != "fullkv"), "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
+        "genlen": args.genlen, "decode_cuda_graph": bool(args.graph and args.method != "fullkv" and tp == 1), "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
         "decode_tok_s": round(args.batch * (args.genlen - 1) / (dec / 1e3), 1),
         "reference_throughput_tok_s": round((args.genlen - 1) / ((ttft + dec) / 1e3), 2),   # benchmark/e2e.py:183 definition
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2), "data": "random-init weights, all-ones ids",
     }
-    print(json.dumps(line))
+    if rank == 0:
+        print(json.dumps(line))
+    if tp > 1:
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
     return line
 
 

@@ -76,6 +76,29 @@ def run_one(mode, b, l, c, w, ks, pool, reps=10):
     return out
 
 
+def grid(quick=False):
+    """The config-5 grid (shared with ``bench.py --sweep``, which adds the reference-torch-on-this-GPU column)."""
+    base = dict(mode="fastkv", b=1, l=32768, c=2048, w=8, ks=7, pool="avgpool")
+    cfgs = []
+    add = lambda **kw: cfgs.append({**base, **kw})  # noqa: E731
+    for l in ([8192, 32768] if quick else [4096, 8192, 16384, 32768, 65536, 131072]):
+        add(l=l)
+    if not quick:
+        for c in [128, 256, 512, 1024]:
+            add(c=c)
+        for w in [16, 32]:
+            add(w=w)
+        for ks in [5, 13]:
+            add(ks=ks)
+        add(pool="maxpool")
+        add(l=131072, c=128, w=32, ks=13, pool="maxpool")
+        add(b=8, c=512)                                  # config 4 shape
+        for mode in ["snapkv", "gemfilter"]:
+            for l in [32768, 131072]:
+                add(mode=mode, l=l)
+    return cfgs
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
