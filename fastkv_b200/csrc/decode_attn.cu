@@ -176,7 +176,8 @@ decode_attn_kernel(DecodeArgs a) {
       }
       if (lane >= crow) x0 = -INFINITY;
       if (lane + 32 >= crow) x1 = -INFINITY;
-      const float m_old = red[4 * g];
+      float m_old = (lane == 0) ? red[4 * g] : 0.f;   // one lane reads and later rewrites the running max: no intra-warp hazard
+      m_old = __shfl_sync(0xffffffffu, m_old, 0);
       const float m = fmaxf(m_old, warp_max(fmaxf(x0, x1)));
       const float p0 = exp2f(x0 - m), p1 = exp2f(x1 - m);        // exp2(-inf) = 0 for the missing rows
       const float alpha = exp2f(m_old - m);                       // first step: exp2(-inf) = 0

@@ -35,7 +35,9 @@ constexpr int kSelCand = 4096;
 constexpr int kSpinLimit = 1 << 22;               // bounded spin: a broken barrier flags the workspace instead of hanging
 
 // per-row control words in the persistent workspace region (zero between launches)
-enum { kCtlBarH = 0, kCtlBarS = 1, kCtlBarL = 2, kCtlCursor = 3, kCtlDepart = 4, kCtlWords = 8 };
+// (word 2-3 is ONE 64-bit word: low half = list cursor, high half = arrivals at the list barrier, so the CTA that sees
+// the barrier open has the list length from the same load)
+enum { kCtlBarH = 0, kCtlBarS = 1, kCtlList = 2, kCtlDepart = 4, kCtlWords = 8 };
 static_assert(kCtlWords * 4 == 32, "control block size is part of the workspace layout (common.cuh)");
 
 struct SelArgs {
@@ -83,17 +85,36 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
 
 // Per-row barrier between the R CTAs that serve a row: everything this CTA wrote before is visible to the others
 // after.  One thread arrives (release) and spins (acquire); the rest of the CTA waits at the closing __syncthreads.
+// (the arrival is a gpu-scope RELEASE by one thread after the CTA barrier: cumulativity covers the whole CTA's writes,
+// which is cheaper than a membar by every thread)
 __device__ __forceinline__ void row_barrier(uint32_t* counter, uint32_t R, uint32_t* err) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(counter, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     int spins = 0;
     while (ld_acquire_u32(counter) < R) {
       if (++spins > kSpinLimit) { *err = 2u; break; }        // never hang the device: flag the workspace and go on
     }
   }
   __syncthreads();
+}
+
+// The list barrier: arrivals live in the high half of the 64-bit list word; returns the list length (low half).
+__device__ __forceinline__ uint32_t list_barrier(unsigned long long* word, uint32_t R, uint32_t* err, uint32_t* bcast) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(word), "l"(1ull << 32) : "memory");
+    unsigned long long v;
+    int spins = 0;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+      if ((uint32_t)(v >> 32) >= R) break;
+      if (++spins > kSpinLimit) { *err = 2u; break; }
+    }
+    *bcast = (uint32_t)(v & 0xffffffffull);
+  }
+  __syncthreads();
+  return *bcast;
 }
 
 // The slice of the row this CTA scans: f(index, value) for each of its keys (float4 granules, remainder to the last CTA).
@@ -338,7 +359,8 @@ select_compact_kernel(SelArgs a) {
         }
         const uint32_t wtotal = __shfl_sync(0xffffffffu, pre, 31);
         uint32_t wbase = 0;
-        if (lane == 31 && wtotal) wbase = atomicAdd(ctl + kCtlCursor, wtotal);
+        if (lane == 31 && wtotal)
+          wbase = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(ctl + kCtlList), (unsigned long long)wtotal);
         wbase = __shfl_sync(0xffffffffu, wbase, 31);
         uint32_t pos = wbase + pre - mine;
 #pragma unroll
@@ -356,15 +378,14 @@ select_compact_kernel(SelArgs a) {
         if (j < n) {
           const float xv = __ldg(src + j);
           if (by_float ? (xv >= thr_f) : (ordered_key(xv) >= thr)) {
-            const uint32_t pos = atomicAdd(ctl + kCtlCursor, 1u);
+            const uint32_t pos = (uint32_t)atomicAdd(reinterpret_cast<unsigned long long*>(ctl + kCtlList), 1ull);
             if (pos < (uint32_t)kSelCand)
               glist[pos] = ((unsigned long long)ordered_key(xv) << 32) | (uint32_t)(0xffffffffu - (uint32_t)j);
           }
         }
       }
     }
-    row_barrier(ctl + kCtlBarL, R, a.err);
-    n_list = min(ld_acquire_u32(ctl + kCtlCursor), (uint32_t)kSelCand);
+    n_list = min(list_barrier(reinterpret_cast<unsigned long long*>(ctl + kCtlList), R, a.err, &sm.bc[15]), (uint32_t)kSelCand);
     klo = thr; khi = (top_bin << 20) | 0xfffffu;
     for (uint32_t i = tid; i < n_list; i += kThreads) {
       const unsigned long long c = __ldcg(glist + i);

@@ -24,12 +24,24 @@ q, k, v = mk(1, 2048, 32), mk(1, 2048, 8), mk(1, 2048, 8)
 ops.compress(q, k, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=2048)
 os.environ["FKV_SMALL_FUSE"] = "0"
 ops.compress(q, k, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=2048)
+# long rows: producer-built histogram, slice scan, per-row barrier, candidate list, crowded-bin refinement (narrow scores)
+q, k, v = mk(1, 9000, 32), mk(1, 9000, 8), mk(1, 9000, 8)
+ops.compress(q, k, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=512, tsp_len=1024)
+kq = (k * 0.01).contiguous().transpose(1, 2).contiguous().transpose(1, 2)            # flat scores: the threshold bin is crowded
+ops.compress(q, kq, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=2048)
+ov = ops.SelectOverlap(partition=True)                                             # select + compact on a side stream, SM partition
+for _ in range(3):
+    ops.compress(q, k, v, window_size=8, kernel_size=7, pooling="avgpool", capacity=512, overlap=ov)
+ov.join()
 ops.topk(torch.rand(3, 70000, device="cuda"), 30000)
 hid = torch.randn(1, 5000, 1024, device="cuda", dtype=torch.bfloat16)
 ops.gather_rows(hid, torch.arange(0, 5000, 7, device="cuda")[None], torch.arange(5000, device="cuda")[None])
 qd = torch.randn(2, 16, 128, device="cuda", dtype=torch.bfloat16)
 kc = torch.randn(2, 4, 1024, 128, device="cuda", dtype=torch.bfloat16); vc = torch.randn_like(kc)
 ops.cache_append(torch.randn(2, 4, 1, 128, device="cuda", dtype=torch.bfloat16), torch.randn(2, 4, 1, 128, device="cuda", dtype=torch.bfloat16), kc, vc, 900)
-ops.decode_attn(qd, kc, vc, 901)
+ops.decode_attn(qd, kc, vc, 901)                                                    # several splits + in-kernel merge
+ops.decode_attn(qd, kc, vc, 40)                                                     # single CTA per head group
+sl = torch.tensor([901], dtype=torch.int32, device="cuda")
+ops.decode_attn(qd, kc, vc, 0, seq_len_dev=sl)
 torch.cuda.synchronize()
 print("sanitize run done")

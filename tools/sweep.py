@@ -105,24 +105,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/sweep.md")
     ap.add_argument("--peak", type=float, default=6546.2, help="HBM GB/s the fractions are quoted against")
     a = ap.parse_args()
-    base = dict(mode="fastkv", b=1, l=32768, c=2048, w=8, ks=7, pool="avgpool")
-    cfgs = []
-    add = lambda **kw: cfgs.append({**base, **kw})  # noqa: E731
-    for l in ([8192, 32768] if a.quick else [4096, 8192, 16384, 32768, 65536, 131072]):
-        add(l=l)
-    if not a.quick:
-        for c in [128, 256, 512, 1024]:
-            add(c=c)
-        for w in [16, 32]:
-            add(w=w)
-        for ks in [5, 13]:
-            add(ks=ks)
-        add(pool="maxpool")
-        add(l=131072, c=128, w=32, ks=13, pool="maxpool")
-        add(b=8, c=512)                                  # config 4 shape
-        for mode in ["snapkv", "gemfilter"]:
-            for l in [32768, 131072]:
-                add(mode=mode, l=l)
+    cfgs = grid(a.quick)
     rows = ["| mode | B | L | C | W | kernel | pool | score impl | pipeline µs | score stage µs | algorithmic MB | pipeline GB/s | frac of %.0f GB/s |" % a.peak,
             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for c in cfgs:
