@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--capacity", type=int, default=2048)
     ap.add_argument("--tsp-len", type=int, default=2048)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--exchange", default="gather", choices=["gather", "reduce"],
+                    help="N > 1: the TSP layer's exchange: all-gather of the per-head scores (bit-identical selection at every N) "
+                         "or the north star's single fp32 all-reduce of the partial importance")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N prompts, Hkv/N heads of each per rank (default); strong = ONE prompt, Hkv/N heads per rank")
     ap.add_argument("--no-overlap", action="store_true", help="run the select + compact stage on the same stream as the scoring")
@@ -309,7 +312,7 @@ def workload_config(args, n):
                      f"{args.capacity}, window {W}, kernel {KS} {POOL}; step = the 32 update_kv calls of one prefill "
                      f"(+ hidden-state gather at the TSP layer)"),
         "ctx": args.ctx, "capacity": args.capacity, "tsp_len": args.tsp_len, "window": W, "kernel_size": KS,
-        "pooling": POOL, "prompts": n, "sharding": f"kv-heads/{int(os.environ.get('WORLD_SIZE', '1'))}" if int(os.environ.get('WORLD_SIZE', '1')) > 1 else "none",
+        "pooling": POOL, "prompts": n, "exchange": args.exchange if int(os.environ.get('WORLD_SIZE', '1')) > 1 else None, "sharding": f"kv-heads/{int(os.environ.get('WORLD_SIZE', '1'))}" if int(os.environ.get('WORLD_SIZE', '1')) > 1 else "none",
         "l2": "per-layer distinct K/V/Q buffers: each step streams > 2 GB, far above the 126 MB L2",
     }
 
@@ -340,7 +343,7 @@ def run_ours(args):
     hkv_local, hq_local = HKV // world, HQ // world
     ctx, cap, tsp_len = args.ctx, args.capacity, args.tsp_len
     plan = step_plan(ctx, cap, tsp_len)
-    shard = HeadShard(exchange="gather") if world > 1 else None
+    shard = HeadShard(exchange=args.exchange) if world > 1 else None
 
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
 
@@ -678,7 +681,8 @@ def run_sweep(args):
 
     def torch_us(c):
         g = torch.Generator(device=dev).manual_seed(1)
-        mk = lambda h: torch.randn(c["b"], c["l"], h, D, generator=g, device=dev, dtype=torch.bfloat16).transpose(1, 2)
+        dt = torch.float32 if c.get("dtype") == "f32" else torch.bfloat16
+        mk = lambda h: torch.randn(c["b"], c["l"], h, D, generator=g, device=dev, dtype=torch.bfloat16).transpose(1, 2).to(dt)
         q, k, v = mk(HQ), mk(HKV), mk(HKV)
         if c["mode"] == "fastkv":
             fn = lambda: O.fastkv_update_kv(k, q, v, HQ // HKV, window_size=c["w"], max_capacity_prompt=c["c"], kernel_size=c["ks"],
@@ -699,7 +703,7 @@ def run_sweep(args):
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) * 1e3 / 5
 
-    rows = [f"| mode | B | L | C | W | kernel | pool | ours: pipeline µs | ours: score stage µs | reference torch on this GPU µs (bf16, eager) | speed-up | "
+    rows = [f"| mode | B | L | C | W | kernel | pool | ours: pipeline µs | ours: score stage µs | reference torch on this GPU µs (same dtype, eager) | speed-up | "
             f"algorithmic MB | ours GB/s | frac of {peak:.0f} GB/s |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for c in S.grid(quick=False):
         tot, sc = S.run_one(**c)
@@ -709,9 +713,9 @@ def run_sweep(args):
             ref = float("nan")
             print(f"[sweep] torch path failed for {c}: {type(e).__name__}: {e}", file=sys.stderr)
         torch.cuda.empty_cache()
-        nb = S.alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"])
+        nb = S.alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"], e=4 if c.get("dtype") == "f32" else 2)
         gbs = nb / tot / 1e3
-        rows.append(f"| {c['mode']} | {c['b']} | {c['l']} | {c['c']} | {c['w']} | {c['ks']} | {c['pool']} | {tot:.1f} | {sc:.1f} | {ref:.0f} | "
+        rows.append(f"| {c['mode']}{' fp32' if c.get('dtype') == 'f32' else ''} | {c['b']} | {c['l']} | {c['c']} | {c['w']} | {c['ks']} | {c['pool']} | {tot:.1f} | {sc:.1f} | {ref:.0f} | "
                     f"{ref / tot:.1f}x | {nb / 1e6:.1f} | {gbs:.0f} | {gbs / peak:.2f} |")
         print(rows[-1], flush=True)
     os.makedirs(os.path.dirname(args.sweep) or ".", exist_ok=True)

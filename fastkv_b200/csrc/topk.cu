@@ -548,9 +548,9 @@ static int launch_topk_impl(const fkv_topk_params& p, const fkv_gather_kv_params
   if (a.nsum > 1) {
     if (p.imp_out) a.dense = p.imp_out;
     else {
-      if (!ws) return FKV_EWORKSPACE;
-      a.dense = reinterpret_cast<float*>(ws);
       off = align_up((size_t)p.rows * p.n * sizeof(float), 256);
+      if (!ws || p.workspace_bytes < off) return FKV_EWORKSPACE;      // the summed rows live in the caller's scratch
+      a.dense = reinterpret_cast<float*>(ws);
     }
   }
   const bool by_value = p.order == FKV_ORDER_VALUE_DESC;

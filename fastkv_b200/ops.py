@@ -88,8 +88,12 @@ def selection_heads(mode: int, Hq: int, Hkv: int) -> int:
 
 def score(q: torch.Tensor, k: torch.Tensor, *, window_size: int, kernel_size: int, pooling: str = "avgpool",
           mode: int = L.MODE_FASTKV, head_range: Optional[Tuple[int, int]] = None,
-          q_head_range: Optional[Tuple[int, int]] = None, impl: int = L.IMPL_AUTO) -> torch.Tensor:
-    """Pooled, group-summed selection scores [B, h1-h0, P] fp32 (P = L - W; GemFilter: P = L)."""
+          q_head_range: Optional[Tuple[int, int]] = None, impl: int = L.IMPL_AUTO, hist_slot: int = 0,
+          max_ctas: int = 0) -> torch.Tensor:
+    """Pooled, group-summed selection scores [B, h1-h0, P] fp32 (P = L - W; GemFilter: P = L).
+
+    ``hist_slot`` 1 / 2 additionally fills that slot's score-row histograms in the workspace (for a following
+    ``fkv_select_compact``; the caller must then run it, it is what re-zeroes them); ``max_ctas`` caps the grid."""
     L.require_cuda(q, k)
     lib = L.load()
     B, Hq, Lq, _ = q.shape
@@ -104,6 +108,7 @@ def score(q: torch.Tensor, k: torch.Tensor, *, window_size: int, kernel_size: in
     ws = L.workspace(q.device, lib.fkv_workspace_bytes(mode, B, Hq, Hkv, Lq, window_size, window_size + 1, 0))
     pool = L.pool_code(pooling) if mode != L.MODE_GEMFILTER else L.POOL_AVG
     p = _score_params(mode, q, k, window_size, kernel_size, pool, out, h0, h1, qh0, qh1, impl, ws)
+    p.hist_slot, p.max_ctas = hist_slot, max_ctas
     L.check(lib.fkv_score(C.byref(p), L.stream_ptr(q.device)))
     return out
 

@@ -31,10 +31,10 @@ def test_struct_sizes_match_c_layout():
     """ctypes mirrors must have the C sizes (checked against sizes compiled from the header)."""
     import subprocess, tempfile
     from fastkv_b200 import _lib
-    src = '#include <stdio.h>\n#include "fastkv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "fastkv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(fkv_view4),sizeof(fkv_score_params),sizeof(fkv_topk_params),sizeof(fkv_gather_kv_params),' \
           'sizeof(fkv_gather_rows_params),sizeof(fkv_decode_attn_params),sizeof(fkv_cache_append_params),' \
-          'sizeof(fkv_compress_params));return 0;}\n'
+          'sizeof(fkv_compress_params),sizeof(fkv_select_compact_params),(size_t)FKV_WORKSPACE_HEADER_BYTES);return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -42,8 +42,9 @@ def test_struct_sizes_match_c_layout():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [_lib.View4, _lib.ScoreParams, _lib.TopkParams, _lib.GatherKvParams, _lib.GatherRowsParams,
-               _lib.DecodeAttnParams, _lib.CacheAppendParams, _lib.CompressParams]
-    assert sizes == [ctypes.sizeof(m) for m in mirrors]
+               _lib.DecodeAttnParams, _lib.CacheAppendParams, _lib.CompressParams, _lib.SelectCompactParams]
+    assert sizes[:-1] == [ctypes.sizeof(m) for m in mirrors]
+    assert sizes[-1] == _lib.WS_HEADER                         # the persistent region the Python side reserves
 
 
 def test_strerror_and_error_mapping():
@@ -76,7 +77,15 @@ def test_null_and_bad_arguments_return_codes_without_a_gpu():
     assert lib.fkv_score(ctypes.byref(sp), None) == -3          # head_dim 96
     sp.D, sp.kernel_size = 128, 4
     assert lib.fkv_score(ctypes.byref(sp), None) == -4          # even kernel_size
-    assert lib.fkv_workspace_bytes(0, 1, 32, 8, 32768, 8, 2048, 2040) > 0
+    assert lib.fkv_workspace_bytes(0, 1, 32, 8, 32768, 8, 2048, 2040) > _lib.WS_HEADER
+    assert lib.fkv_topk_workspace_bytes(1, 1000, 10) > _lib.WS_HEADER and lib.fkv_decode_workspace_bytes(1, 32, 128, 2304) > _lib.WS_HEADER
+    sc = _lib.SelectCompactParams()
+    assert lib.fkv_select_compact(ctypes.byref(sc), None) == -1     # struct_size guard
+    assert lib.fkv_select_compact(None, None) == -1
+    assert lib.fkv_workspace_status(None, None) == -7               # FKV_EWORKSPACE
+    sp.D, sp.kernel_size, sp.hist_slot = 128, 7, 3
+    sp.pooling, sp.window_size, sp.h1 = 0, 8, 2
+    assert lib.fkv_score(ctypes.byref(sp), None) in (-1, -6, -7)    # rejected before any launch (null views / workspace / bad slot)
 
 
 def test_early_return_is_by_reference_and_needs_no_gpu():

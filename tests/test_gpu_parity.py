@@ -319,6 +319,70 @@ def test_uninitialised_workspace_fails_loudly():
     assert "FAILED LOUDLY" in r.stdout and "NO ERROR" not in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
 
 
+@pytest.mark.parametrize("l,c,t", [(9000, 512, 1024), (2048, 2048, 0), (33000, 2048, 2048), (5000, 256, 0)])
+def test_overlapped_select_equals_the_serial_call(l, c, t):
+    """ops.SelectOverlap: scoring on the caller's stream, select + compact on a side stream (two histogram slots, SM
+    partition) — eagerly and captured in a CUDA graph — must give exactly the serial results."""
+    from fastkv_b200 import ops
+    q, k, v = [x.to(DEV) for x in make_inputs(l, 1, 32, 8, l, 128)]
+    kw = dict(window_size=8, kernel_size=7, pooling="avgpool", capacity=c, tsp_len=t, return_aux=True)
+    ref = ops.compress(q, k, v, **kw)
+    for partition in (False, True):
+        ov = ops.SelectOverlap(partition=partition)
+        outs = [ops.compress(q, k, v, overlap=ov, **kw) for _ in range(3)]        # slots 1, 2, 1: the third call waits for the first
+        ov.join()
+        torch.cuda.synchronize()
+        for got in outs:
+            assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]) and torch.equal(ref[3]["idx"], got[3]["idx"])
+            assert (ref[2] is None and got[2] is None) or torch.equal(ref[2], got[2])
+    ov = ops.SelectOverlap(partition=True)
+    ko, vo = torch.empty_like(ref[0]), torch.empty_like(ref[1])
+    ops.compress(q, k, v, overlap=ov, k_out=ko, v_out=vo, **kw); ov.join(); torch.cuda.synchronize()      # warm-up
+    ko.zero_(); vo.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(2):
+            ops.compress(q, k, v, overlap=ov, k_out=ko, v_out=vo, **kw)
+        ov.join()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(ko, ref[0]) and torch.equal(vo, ref[1])
+    from fastkv_b200 import _lib as LL
+    assert LL.workspace_status(torch.device(DEV, torch.cuda.current_device())) == 0      # no barrier time-out was flagged
+
+
+def test_select_compact_entry_point_builds_its_own_histogram():
+    """fkv_select_compact with have_hist = 0 (what the fp32 scoring path gets): the CTAs build the row histograms from
+    their slices first.  Long rows, bf16 K/V, scores from the tensor-core kernel WITHOUT a histogram slot."""
+    import ctypes as C
+    from fastkv_b200 import ops
+    L = _lib()
+    lib = L.load()
+    b, hq, hkv, l, d, w, cap = 2, 16, 4, 12000, 128, 8, 520
+    q, k, v = [x.to(DEV) for x in make_inputs(5, b, hq, hkv, l, d)]
+    score = ops.score(q, k, window_size=w, kernel_size=7, pooling="avgpool")             # [B, Hkv, P], no histogram
+    n_sel, p = cap - w, l - w
+    idx = torch.empty(b, hkv, n_sel, dtype=torch.int64, device=DEV)
+    ko = torch.empty(b, hkv, cap, d, dtype=k.dtype, device=DEV)
+    vo = torch.empty_like(ko)
+    ws = L.workspace(q.device, lib.fkv_workspace_bytes(L.MODE_FASTKV, b, hq, hkv, l, w, cap, 0))
+    sc = L.SelectCompactParams()
+    sc.struct_size = C.sizeof(L.SelectCompactParams)
+    sc.hist_slot, sc.have_hist = 2, 0
+    sc.score, sc.idx_out = score.data_ptr(), idx.data_ptr()
+    g = sc.gather
+    g.struct_size = C.sizeof(L.GatherKvParams)
+    g.dtype, g.B, g.L, g.D, g.window_size, g.n_sel, g.h0, g.h1, g.head_div = L.dtype_code(k.dtype), b, l, d, w, n_sel, 0, hkv, 1
+    g.k, g.v, g.k_out, g.v_out = L.view4(k), L.view4(v), L.view4(ko), L.view4(vo)
+    sc.workspace, sc.workspace_bytes = ws.data_ptr(), ws.numel()
+    for _ in range(2):                                                                   # twice: the tables must come back clean
+        L.check(lib.fkv_select_compact(C.byref(sc), L.stream_ptr(q.device)))
+    torch.cuda.synchronize()
+    check_topk_consistent(score, idx, "select_compact, own histogram")
+    check_compaction_exact(k, v, idx, ko, vo, w)
+    assert L.workspace_status(q.device) == 0
+
+
 def test_strided_blhd_views_equal_contiguous_inputs():
     """update_kv gets [B,H,L,D] views of [B,L,H,D] memory; results must not depend on the layout."""
     knobs = dict(window_size=8, max_capacity_prompt=128, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=256)

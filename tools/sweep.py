@@ -27,15 +27,16 @@ def alg_bytes(mode, b, l, c, w, e=2):
             + 2 * 2 * b * hsel * c * D * e)
 
 
-def make(b, l, h, g):
-    return torch.randn(b, l, h, D, generator=g, device="cuda", dtype=torch.bfloat16).transpose(1, 2)
+def make(b, l, h, g, dtype=torch.bfloat16):
+    return torch.randn(b, l, h, D, generator=g, device="cuda", dtype=torch.bfloat16).transpose(1, 2).to(dtype)
 
 
-def run_one(mode, b, l, c, w, ks, pool, reps=10):
+def run_one(mode, b, l, c, w, ks, pool, reps=10, dtype="bf16"):
+    dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[dtype]
     g = torch.Generator(device="cuda").manual_seed(42)
     kbytes = b * l * HKV * D * 2
     nbuf = max(2, min(6, int(300e6 // kbytes) + 1))
-    bufs = [(make(b, l, HQ, g), make(b, l, HKV, g), make(b, l, HKV, g)) for _ in range(nbuf)]
+    bufs = [(make(b, l, HQ, g, dt), make(b, l, HKV, g, dt), make(b, l, HKV, g, dt)) for _ in range(nbuf)]
     code = {"fastkv": L.MODE_FASTKV, "snapkv": L.MODE_SNAPKV, "gemfilter": L.MODE_GEMFILTER}[mode]
 
     def call(q, k, v):
@@ -93,6 +94,7 @@ def grid(quick=False):
         add(pool="maxpool")
         add(l=131072, c=128, w=32, ks=13, pool="maxpool")
         add(b=8, c=512)                                  # config 4 shape
+        add(l=8192, c=512, dtype="f32")                  # BASELINE configs[0] on the GPU: fp32 inputs, CUDA-core scoring path
         for mode in ["snapkv", "gemfilter"]:
             for l in [32768, 131072]:
                 add(mode=mode, l=l)
@@ -110,11 +112,13 @@ def main():
             "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for c in cfgs:
         tot, sc = run_one(**c)
-        nb = alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"])
+        nb = alg_bytes(c["mode"], c["b"], c["l"], c["c"], c["w"], e=4 if c.get("dtype") == "f32" else 2)
         impl = "tcgen05"
         if impl == "tcgen05" and c["w"] * (HQ // HKV) > 32:
             impl += " x%d head groups" % (c["w"] * (HQ // HKV) // 32)
         gbs = nb / tot / 1e3
+        if c.get("dtype") == "f32":
+            impl = "fp32 CUDA cores"
         rows.append(f"| {c['mode']} | {c['b']} | {c['l']} | {c['c']} | {c['w']} | {c['ks']} | {c['pool']} | {impl} | {tot:.1f} | {sc:.1f} | "
                     f"{nb / 1e6:.1f} | {gbs:.0f} | {gbs / a.peak:.2f} |")
         print(rows[-1], flush=True)
