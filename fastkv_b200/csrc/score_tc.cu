@@ -378,7 +378,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       for (int c0 = sub; c0 < cnt; c0 += 32) {
         unsigned long long w0[4], w1[4];
         bool ok;
+        int spins = 0;
         do {
+          // bounded: a partner CTA that never becomes resident (two persistent grids over-subscribing the chip) must
+          // not hang the device; flag the workspace (fkv_workspace_status) and go on with what is there
+          if (++spins > (1 << 22)) { a.sync_counter[5] = 3u; break; }
           ok = true;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {

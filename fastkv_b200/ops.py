@@ -28,8 +28,11 @@ class SelectOverlap:
     def __init__(self, device=None, partition: bool = False):
         """``partition``: split the SMs between the scoring kernel on the caller's stream and the select + compact
         kernel on the side stream (back-to-back update_kv calls, as in bench.py: both kernels are persistent and
-        latency-bound, so each loses little with fewer SMs and they truly run side by side).  Leave it off when other
-        work (attention, MLP) sits between the calls: the stage then simply fills SMs as they become free."""
+        latency-bound, so each loses little with fewer SMs and they truly run side by side).
+        Without it the two kernels are never allowed to run at the same time (the next scoring kernel waits for the
+        previous select stage): both are persistent kernels whose CTAs wait for each other, and two such grids that do
+        not FIT the chip together can starve each other of SMs.  The stage then overlaps only what the caller does
+        between two calls (attention, MLP), which is the case in a model forward."""
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         sms = torch.cuda.get_device_properties(self.device).multi_processor_count
         self.select_ctas = min(self.SELECT_CTAS, sms // 2) if partition else 0
@@ -215,7 +218,11 @@ def _compress_overlapped(lib, ov, mode, q, k, v, W, kernel_size, pooling, capaci
     Hsel, P, n_sel = h1 - h0, Lq - W, capacity - W
     main = torch.cuda.current_stream(dev)
     slot = ov.next_slot()
-    if ov.done[slot - 1] is not None:                  # the call that used this slot's tables two calls ago
+    if ov.select_ctas == 0:                            # no SM partition: never co-schedule the two persistent kernels
+        for ev in ov.done:
+            if ev is not None:
+                main.wait_event(ev)
+    elif ov.done[slot - 1] is not None:                # the call that used this slot's tables two calls ago
         main.wait_event(ov.done[slot - 1])
     sp = _score_params(mode, q, k, W, kernel_size, L.pool_code(pooling), score_buf, h0, h1, 0, 0, impl, ws)
     sp.hist_slot = slot if P > 4096 else 0

@@ -327,15 +327,29 @@ def test_overlapped_select_equals_the_serial_call(l, c, t):
     q, k, v = [x.to(DEV) for x in make_inputs(l, 1, 32, 8, l, 128)]
     kw = dict(window_size=8, kernel_size=7, pooling="avgpool", capacity=c, tsp_len=t, return_aux=True)
     ref = ops.compress(q, k, v, **kw)
+
+    def same_as_serial(got):
+        assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]) and torch.equal(ref[3]["idx"], got[3]["idx"])
+        assert (ref[2] is None and got[2] is None) or torch.equal(ref[2], got[2])
+
+    def consistent(got):
+        # a capped scoring grid splits the keys over fewer CTAs: the fp32 partial sums merge in another order, so the
+        # scores agree to rounding (not bit for bit) and everything downstream must be exact GIVEN those scores
+        check_scores_close(ref[3]["score"], got[3]["score"], 1e-5, "partitioned")
+        check_topk_consistent(got[3]["score"], got[3]["idx"], "partitioned")
+        check_compaction_exact(k, v, got[3]["idx"], got[0], got[1], 8)
+        if t:
+            check_tsp_consistent(got[3]["importance"], got[2], 8, "partitioned")
+
     for partition in (False, True):
         ov = ops.SelectOverlap(partition=partition)
         outs = [ops.compress(q, k, v, overlap=ov, **kw) for _ in range(3)]        # slots 1, 2, 1: the third call waits for the first
         ov.join()
         torch.cuda.synchronize()
         for got in outs:
-            assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]) and torch.equal(ref[3]["idx"], got[3]["idx"])
-            assert (ref[2] is None and got[2] is None) or torch.equal(ref[2], got[2])
-    ov = ops.SelectOverlap(partition=True)
+            (consistent if partition else same_as_serial)(got)
+        assert all(torch.equal(outs[0][0], o[0]) and torch.equal(outs[0][3]["idx"], o[3]["idx"]) for o in outs[1:])   # deterministic
+    ov = ops.SelectOverlap(partition=False)
     ko, vo = torch.empty_like(ref[0]), torch.empty_like(ref[1])
     ops.compress(q, k, v, overlap=ov, k_out=ko, v_out=vo, **kw); ov.join(); torch.cuda.synchronize()      # warm-up
     ko.zero_(); vo.zero_()
