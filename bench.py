@@ -638,7 +638,7 @@ def run_ours(args):
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import model_bench
             margs = _types.SimpleNamespace(model="llama", method="fastkv", ctx=ctx, batch=1, genlen=64, capacity=cap,
-                                           tsp_len=tsp_len, tsp_idx=TSP_IDX, layers=0, runs=1, graph=True)
+                                           tsp_len=tsp_len, tsp_idx=TSP_IDX, layers=0, runs=2, graph=True)
             import io, contextlib
             with contextlib.redirect_stdout(io.StringIO()):
                 model_extras = model_bench.run(margs)

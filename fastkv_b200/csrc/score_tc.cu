@@ -17,8 +17,9 @@
 //            records of the CTAs that share them (no grid barrier: records validate themselves)
 //   pass 2   p = exp2(x - max) / sum from the logits in TMEM -> votes per query head -> pool1d over the
 //            halo'd tile -> group-sum -> score[b, h, j]; reading a tile frees its TMEM block for the next phase
-// Warp roles (448 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (both stream
-// through all phases without stopping), warps 2-13 = three epilogue warpgroups taking tiles round-robin.
+// Warp roles (512 threads = 4 aligned warpgroups): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM allocator (both stream
+// through all phases without stopping), warps 2-3 idle, warps 4-15 = three epilogue warpgroups taking tiles round-robin;
+// setmaxnreg moves registers from the control warpgroup (80 per thread) to the epilogue (144 per thread).
 #include "tc_common.cuh"
 
 namespace fkv {
@@ -65,7 +66,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   static_assert(N <= 32 && (N & 7) == 0, "unsupported window x group size");
 
   extern __shared__ unsigned char smem_dyn[];
-  if (threadIdx.x == 64) FKV_TRACE(0);
+  if (threadIdx.x == kCtrlThreads) FKV_TRACE(0);
   const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sm = smem_dyn + (base - smem_u32(smem_dyn));
 
@@ -123,8 +124,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_enter();                                      // nothing global is touched before this point
-  if (threadIdx.x == 64) FKV_TRACE(1);
+  if (threadIdx.x == kCtrlThreads) FKV_TRACE(1);
+  // register re-allocation between the aligned warpgroups: the control warpgroup keeps 80 registers per thread, the
+  // three epilogue warpgroups get 144 (the 128-register cap of a 512-thread block left the epilogue spilling)
+  // (each setmaxnreg sits at the top of the region it governs, like CUTLASS' warpgroup_reg_dealloc / _alloc)
 
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kCtrlRegs));
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     // One thread; everything in the loop is incremental (no divisions, no local arrays): at
@@ -229,9 +235,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         }
       }
     }
+  }
   } else {
     // ===================================== epilogue =========================================
-    const int et = threadIdx.x - 64;                 // 0..255
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kEpiRegs));
+    const int et = threadIdx.x - kCtrlThreads;       // 0..383
     const int ew = et >> 5;                          // epilogue warp 0..7
     const int wg = ew >> 2;                          // warpgroup: tiles are dealt round-robin
     const int quarter = warp & 3;                    // TMEM lane quarter this warp may access
@@ -378,11 +386,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       for (int c0 = sub; c0 < cnt; c0 += 32) {
         unsigned long long w0[4], w1[4];
         bool ok;
-        int spins = 0;
+        // (this wait is unbounded: a spin counter here was measured at +0.5 us at 32k and +11 us for B = 8 x 32k — the
+        // kernel is that sensitive to its instruction footprint.  Its partners are always resident: the launch is
+        // cooperative and callers never co-schedule another persistent grid unless both fit the chip, ops.SelectOverlap)
         do {
-          // bounded: a partner CTA that never becomes resident (two persistent grids over-subscribing the chip) must
-          // not hang the device; flag the workspace (fkv_workspace_status) and go on with what is there
-          if (++spins > (1 << 22)) { a.sync_counter[5] = 3u; break; }
           ok = true;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -507,7 +514,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     }                                                // phases
   }
 
-  if (threadIdx.x == 64) {
+  if (threadIdx.x == kCtrlThreads) {
     FKV_TRACE(7);
     // departure count: the last CTA out resets it and advances the epoch, so the next launch on this
     // stream needs no memset node in front of it and can tell its own records from older ones
@@ -520,7 +527,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 64) FKV_TRACE(8);
+  if (threadIdx.x == kCtrlThreads) FKV_TRACE(8);
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }

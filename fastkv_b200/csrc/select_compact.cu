@@ -311,16 +311,9 @@ select_compact_kernel(SelArgs a) {
   } else {
     uint32_t n_list, klo, khi;
     const uint32_t rmask = R - 1u;
-    const int lines = (a.row_chunks * 16) >> 7;      // 128-byte lines per K (or V) row
-    auto prefetch_rows = [&](uint32_t tok) {         // owned candidate: its K / V rows on their way to L2 while we rank
-      for (int ln = 0; ln < lines; ++ln) {
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(kb + (int64_t)tok * a.k_sl + ln * 128));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (int64_t)tok * a.v_sl + ln * 128));
-      }
-    };
+    // (L2 prefetches of the owned candidates' K / V rows at this point were measured: no gain, 20.5 vs 20.6 us)
     if (small) {
       n_list = (uint32_t)n; klo = sm.bc[13]; khi = sm.bc[14];
-      for (uint32_t j = tid; j < n_list; j += kThreads) if ((j & rmask) == r) prefetch_rows(j);
     } else {
     // ---- C. publish this slice's candidates in the row's list (one cursor atomic per warp and load round) --------
     const float thr_f = key_to_float(thr);
@@ -388,10 +381,7 @@ select_compact_kernel(SelArgs a) {
     n_list = min(list_barrier(reinterpret_cast<unsigned long long*>(ctl + kCtlList), R, a.err, &sm.bc[15]), (uint32_t)kSelCand);
     klo = thr; khi = (top_bin << 20) | 0xfffffu;
     for (uint32_t i = tid; i < n_list; i += kThreads) {
-      const unsigned long long c = __ldcg(glist + i);
-      sm.list[i] = c;
-      const uint32_t tok = 0xffffffffu - (uint32_t)(c & 0xffffffffull);
-      if ((tok & rmask) == r) prefetch_rows(tok);
+      sm.list[i] = __ldcg(glist + i);
     }
     __syncthreads();
     }                                               // !small
