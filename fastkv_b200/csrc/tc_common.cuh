@@ -22,7 +22,7 @@ constexpr int kEpiWarps = 4 * kNumWG;
 constexpr int kCtrlThreads = 128;          // warpgroup 0: warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-3 idle
 constexpr int kTcThreads = kCtrlThreads + kEpiThreads;   // four ALIGNED warpgroups, so that setmaxnreg can move registers
                                                          // from the two single-thread control warps to the epilogue
-constexpr int kCtrlRegs = 80, kEpiRegs = 144;            // 128 * 80 + 384 * 144 = 65536 = 512 * 128
+constexpr int kCtrlRegs = 56, kEpiRegs = 152;            // 128 * 56 + 384 * 152 = 65536 = 512 * 128
 constexpr int kMaxLocalPairs = 8;
 constexpr int kMaxStages = 6;
 constexpr int kMaxPhases = 512;            // (b, h) pairs are processed in groups whose logits fit in TMEM
