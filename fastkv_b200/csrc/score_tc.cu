@@ -84,6 +84,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
   int* ncontrib = reinterpret_cast<int*>(vbuf + kNumWG * 2 * G * kTile);     // [maxlp] CTAs contributing to each local pair
   int* ph_u0 = ncontrib + kMaxLocalPairs;                               // [nph] first unit of this CTA's slice of the phase
   int* ph_T = ph_u0 + kMaxPhases;                                       // [nph] tiles of this CTA in the phase
+  // pass 1 leaves exp2(x*c - ref) in TMEM instead of the logits; ref = the owning warp's running reference at that time
+  float* tile_ref = reinterpret_cast<float*>(ph_T + kMaxPhases);        // [NB][4 warps][N] references a tile's values are relative to
+  unsigned int* tile_ver = reinterpret_cast<unsigned int*>(tile_ref + NB * 4 * N);   // [NB][4] version of those references
+  float* cstage = reinterpret_cast<float*>(tile_ver + NB * 4);          // [epilogue warps][N] coefficient staging (pass 2)
 
   auto bar_full = [&](int s) { return smem_u32(bars + s); };
   auto bar_empty = [&](int s) { return smem_u32(bars + 6 + s); };
@@ -250,6 +254,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     float mn[N], z[N];
 #pragma unroll
     for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+    unsigned int ref_ver = 1u;                       // bumped whenever this warp's references change (pass 1)
     // The host side refuses workspaces that never went through fkv_workspace_init (FKV_EWORKSPACE).  Should the
     // header be overwritten afterwards, never abort the context across the ABI: flag it in the header's error word
     // (read back by fkv_workspace_status) and carry on; the launch stays self-consistent (all CTAs read one epoch).
@@ -273,6 +278,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     const int Uph = min(a.ppp, a.npairs - p0) * a.n_tiles;
 #pragma unroll
     for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+    ++ref_ver;
     int flushed = 0;                                 // local pairs already flushed by this warpgroup
     auto flush_upto = [&](int lp_end) {              // flush local pairs [flushed, lp_end)
       for (; flushed < lp_end; ++flushed) {
@@ -304,6 +310,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         }
 #pragma unroll
         for (int n = 0; n < N; ++n) { mn[n] = kEmptyMax; z[n] = 0.f; }
+        ++ref_ver;
         named_bar(2, kEpiThreads);
         if (et < N) {
           float M = kEmptyMax;
@@ -339,6 +346,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       tmem_load_row<N>(my_tmem + blk * NMMA, s);
       tmem_wait_ld();
       const int key = t * a.S - a.half + row;
+      const bool valid = (key >= 0) && (key < a.L);  // a real key (own or pooling halo)
       const bool own = (row >= a.half) && (row < a.half + a.S) && (key < a.L);
       const bool has_window = (t * a.S - a.half + kTile > a.P);   // warp-uniform
       const int kp = key - a.P;                      // window key index (>= 0 inside the window)
@@ -347,26 +355,38 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
 #pragma unroll
         for (int n = 0; n < N; ++n) s[n] = (kp > (n % W)) ? -INFINITY : s[n];
       }
-      // cheap check first: does any owned key exceed its row's reference by more than tau?
+      // cheap check first: does any key of the tile exceed its row's reference by more than tau?
       float dmax = -INFINITY;
 #pragma unroll
       for (int n = 0; n < N; ++n) dmax = fmaxf(dmax, fmaf(s[n], a.c, -mn[n]));
-      if (__any_sync(0xffffffffu, own && dmax > kLazyTau)) {
+      if (__any_sync(0xffffffffu, valid && dmax > kLazyTau)) {
         // rare (always on the first tile of a pair): raise the references to the warp-wide column max
 #pragma unroll
         for (int n = 0; n < N; ++n) {
-          const float nm = fmaxf(mn[n], warp_max_f32(own ? s[n] * a.c : -INFINITY));
+          const float nm = fmaxf(mn[n], warp_max_f32(valid ? s[n] * a.c : -INFINITY));
           z[n] *= ex2(mn[n] - nm);
           mn[n] = nm;
         }
+        ++ref_ver;
       }
+      // the tile's values go back to TMEM as e = exp2(x*c - ref): pass 2 is then one FMA per value, no MUFU
+#pragma unroll
+      for (int n = 0; n < N; ++n) s[n] = valid ? ex2(fmaf(s[n], a.c, -mn[n])) : 0.f;
+      tmem_store_row<N>(my_tmem + blk * NMMA, s);
       if (own) {
 #pragma unroll
-        for (int n = 0; n < N; ++n) z[n] += ex2(fmaf(s[n], a.c, -mn[n]));
+        for (int n = 0; n < N; ++n) z[n] += s[n];
+      }
+      if (lane == 0) {                               // the references are warp-uniform: one lane records them for pass 2
+        float4* dst = reinterpret_cast<float4*>(tile_ref + (blk * 4 + quarter) * N);
+#pragma unroll
+        for (int n = 0; n < N; n += 4) dst[n >> 2] = make_float4(mn[n], mn[n + 1], mn[n + 2], mn[n + 3]);
+        tile_ver[blk * 4 + quarter] = ref_ver;
       }
       t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
+    tmem_wait_st();                                  // this thread's stores to TMEM are complete before pass 2 reads them
     if (et == 0 && ph == nph - 1) FKV_TRACE(4);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
@@ -423,15 +443,26 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     // ---------------- pass 2: votes -> pool -> group sum -> score ------------------------------
     // every tile of the phase is still resident in TMEM; reading it frees the block for the next phase
     int cur_lp = -1, b = 0, kvl = 0;
+    unsigned int cur_ver = 0u;                       // version of the references the coefficients in mn[] belong to
     { const int u = u0 + wg; pair = u / a.n_tiles; t = u - pair * a.n_tiles; }
     for (int j2 = wg; j2 < T; j2 += kNumWG) {
       const int lp = pair - pair0;
       const int blk = (jbase + j2) & (NB - 1);
-      if (lp != cur_lp) {                            // (max, 1/sum) of this pair's rows -> registers
-        cur_lp = lp;
-        b = pair / a.nkv; kvl = pair - b * a.nkv;
+      if (lp != cur_lp) { b = pair / a.nkv; kvl = pair - b * a.nkv; }
+      // coefficient of column n for this tile: exp2(ref_n - max_n) / sum_n; it changes only when the warp's references
+      // did (about once per pair), so it normally stays in registers from tile to tile
+      const unsigned int ver = tile_ver[blk * 4 + quarter];
+      if (ver != cur_ver || lp != cur_lp) {           // warp-uniform
+        if (lane < N) {
+          const float2 st = colstat[lp * N + lane];
+          cstage[ew * N + lane] = ex2(tile_ref[(blk * 4 + quarter) * N + lane] - st.x) * st.y;
+        }
+        __syncwarp();
+        const float4* cs = reinterpret_cast<const float4*>(cstage + ew * N);
 #pragma unroll
-        for (int n = 0; n < N; ++n) { const float2 v = colstat[lp * N + n]; mn[n] = v.x; z[n] = v.y; }
+        for (int n = 0; n < N; n += 4) { const float4 c4 = cs[n >> 2]; mn[n] = c4.x; mn[n + 1] = c4.y; mn[n + 2] = c4.z; mn[n + 3] = c4.w; }
+        __syncwarp();
+        cur_ver = ver; cur_lp = lp;
       }
       float s[N];
       tmem_load_row<N>(my_tmem + blk * NMMA, s);
@@ -446,7 +477,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
         float vote = 0.f;
 #pragma unroll
         for (int r = 0; r < W; ++r)                  // rows summed in order (utils.py:104)
-          vote = fmaf(ex2(fmaf(s[g * W + r], a.c, -mn[g * W + r])), z[g * W + r], vote);
+          vote = fmaf(s[g * W + r], mn[g * W + r], vote);
         vb[g * kTile + row] = in_prefix ? vote : (kDef ? 0.f : pad);
       }
       named_bar(3 + wg, 128);
@@ -592,8 +623,10 @@ Plan make_plan(const fkv_score_params& p) {
   const int NMMA = pl.N < 16 ? 16 : pl.N;
   const size_t tile_bytes = (size_t)kTile * p.D * 2;
   const size_t q_bytes = ((size_t)NMMA * p.D * 2 + 1023) & ~(size_t)1023;
+  const size_t NBp = 512 / NMMA;
   const size_t misc = 80 * 8 + 16 + (size_t)kEpiWarps * pl.N * 8 + (size_t)kMaxLocalPairs * pl.N * 8 + (size_t)kNumWG * 2 * pl.G * kTile * 4 +
-                      kMaxLocalPairs * 4 + 2 * kMaxPhases * 4;
+                      kMaxLocalPairs * 4 + 2 * kMaxPhases * 4 +
+                      NBp * 4 * pl.N * 4 + NBp * 4 * 4 + (size_t)kEpiWarps * pl.N * 4;   // tile references + versions + coefficient staging
   const size_t budget = 227 * 1024 - 1024 - 2 * q_bytes - misc - 256;
   int nst = (int)(budget / tile_bytes);
   if (nst > kMaxStages) nst = kMaxStages;
