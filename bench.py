@@ -17,8 +17,9 @@ gathering the hidden states, the later layers at tsp_len tokens) on synthetic bf
   cpu_baseline  the oracle port (torch CPU, same ATen ops as the reference) on this box's cores
 
 N > 1 (torchrun): weak scaling — N prompts, every rank owns Hkv/N KV heads of all of them, and
-the TSP layer does the path's one exchange (NCCL all-gather of the per-head scores) before the
-global top-k.  ``--impl reference`` times the oracle port only (rank 0).
+the TSP layer does the path's one exchange before the global top-k: the per-head score rows go
+straight into the peers' HBM (fkv_exchange_push / _wait over NVLink peer memory, inside the step's
+CUDA graph); NCCL all-gather when no peer memory can be mapped.  ``--impl reference`` times the oracle port only (rank 0).
 """
 import argparse
 import json
@@ -52,9 +53,10 @@ def parse():
     ap.add_argument("--capacity", type=int, default=2048)
     ap.add_argument("--tsp-len", type=int, default=2048)
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--exchange", default="gather", choices=["gather", "reduce"],
-                    help="N > 1: the TSP layer's exchange: all-gather of the per-head scores (bit-identical selection at every N) "
-                         "or the north star's single fp32 all-reduce of the partial importance")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "p2p", "gather", "reduce"],
+                    help="N > 1: the TSP layer's exchange: p2p = the library's own stores into peer memory (auto: when peer memory "
+                         "can be mapped, else gather), gather = NCCL all-gather of the per-head scores (both bit-identical selection "
+                         "at every N), reduce = the north star's single fp32 all-reduce of the partial importance")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = N prompts, Hkv/N heads of each per rank (default); strong = ONE prompt, Hkv/N heads per rank")
     ap.add_argument("--no-overlap", action="store_true", help="run the select + compact stage on the same stream as the scoring")
@@ -343,7 +345,21 @@ def run_ours(args):
     hkv_local, hq_local = HKV // world, HQ // world
     ctx, cap, tsp_len = args.ctx, args.capacity, args.tsp_len
     plan = step_plan(ctx, cap, tsp_len)
-    shard = HeadShard(exchange=args.exchange) if world > 1 else None
+    shard = None
+    if world > 1:
+        if args.exchange in ("auto", "p2p"):
+            from fastkv_b200.peer import PeerRegion
+            try:                                        # collective: either every rank gets a region or every rank raises
+                region = PeerRegion(PeerRegion.bytes_for(n_prompts, HKV, ctx - W))
+                shard = HeadShard(exchange="p2p", region=region)
+                args.exchange = f"p2p ({region.backend})"
+            except RuntimeError as e:
+                if args.exchange == "p2p":
+                    raise
+                print(f"[bench] no peer memory ({e}); falling back to the NCCL all-gather", file=sys.stderr)
+                args.exchange = "gather"
+        if shard is None:
+            shard = HeadShard(exchange=args.exchange)
 
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
 
@@ -410,14 +426,16 @@ def run_ours(args):
     run = one_step
     if not args.no_graph:
         try:
-            if world == 1:
+            if world == 1 or args.exchange.startswith("p2p"):
+                # (N > 1 with the p2p exchange: nothing in the step leaves the device, so the whole step is one graph too;
+                # the ranks meet inside it, at the exchange's flags)
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph):
                     one_step()
                 graph.replay()
                 torch.cuda.synchronize()
                 run = graph.replay
-                timed_with = "cuda-graph replay of the C-ABI launches"
+                timed_with = "cuda-graph replay of the C-ABI launches" + (" (peer-memory score exchange inside the graph)" if world > 1 else "")
             elif os.environ.get("FKV_BENCH_NCCL_IN_GRAPH", "0") == "1" and _try_full_graph(one_step) is not None:
                 graph = _try_full_graph.graph
                 run = graph.replay
@@ -664,6 +682,8 @@ def run_ours(args):
         if hasattr(_try_full_graph, "graph"):
             del _try_full_graph.graph
         torch.cuda.synchronize()
+        if shard is not None and shard.region is not None:
+            shard.region.close()                        # collective (barrier inside): nobody unmaps while a peer may still store
         dist.barrier()
         dist.destroy_process_group()
 

@@ -14,13 +14,16 @@ import torch
 from . import _build
 
 # ---- enums (mirror include/fastkv_b200.h) -----------------------------------------------------
-ABI_VERSION = 4
+ABI_VERSION = 5
 BF16, F16, F32 = 0, 1, 2
 POOL_AVG, POOL_MAX = 0, 1
 MODE_FASTKV, MODE_SNAPKV, MODE_GEMFILTER = 0, 1, 2
 ORDER_VALUE_DESC, ORDER_INDEX_ASC = 0, 1
 IMPL_AUTO, IMPL_SIMPLE, IMPL_TENSOR = 0, 1, 2
 EPOOL = -4
+ETIMEOUT = -11
+MAX_PEERS = 8
+EXCHANGE_HEADER = 256                      # FKV_EXCHANGE_HEADER_BYTES
 
 _DTYPES = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
 _POOLS = {"avgpool": POOL_AVG, "maxpool": POOL_MAX}
@@ -120,12 +123,24 @@ class CompressParams(C.Structure):
     ]
 
 
+class ExchangeParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32),
+        ("B", C.c_int32), ("heads_local", C.c_int32), ("P", C.c_int64),
+        ("score", C.c_void_p), ("score_stride_b", C.c_int64), ("score_stride_h", C.c_int64),
+        ("region", C.c_void_p * 8), ("region_bytes", C.c_size_t),
+        ("max_ctas", C.c_int32), ("timeout_ms", C.c_int32),
+    ]
+
+
 EXPORTS = [
     "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_workspace_status",
     "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
     "fkv_score_impl_name", "fkv_launch_count",
     "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_select_compact", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append",
     "fkv_compress",
+    "fkv_exchange_push", "fkv_exchange_wait", "fkv_exchange_status",
+    "fkv_peer_alloc", "fkv_peer_open", "fkv_peer_close", "fkv_peer_free",
 ]
 
 _lib = None
@@ -165,10 +180,21 @@ def load():
         for name, st in [("fkv_score", ScoreParams), ("fkv_topk", TopkParams), ("fkv_gather_kv", GatherKvParams),
                          ("fkv_select_compact", SelectCompactParams),
                          ("fkv_gather_rows", GatherRowsParams), ("fkv_decode_attn", DecodeAttnParams),
-                         ("fkv_cache_append", CacheAppendParams), ("fkv_compress", CompressParams)]:
+                         ("fkv_cache_append", CacheAppendParams), ("fkv_compress", CompressParams),
+                         ("fkv_exchange_push", ExchangeParams), ("fkv_exchange_wait", ExchangeParams)]:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(st), C.c_void_p]
+        lib.fkv_exchange_status.restype = C.c_int
+        lib.fkv_exchange_status.argtypes = [C.c_void_p, C.c_void_p]
+        lib.fkv_peer_alloc.restype = C.c_int
+        lib.fkv_peer_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_char_p]
+        lib.fkv_peer_open.restype = C.c_int
+        lib.fkv_peer_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        lib.fkv_peer_close.restype = C.c_int
+        lib.fkv_peer_close.argtypes = [C.c_void_p]
+        lib.fkv_peer_free.restype = C.c_int
+        lib.fkv_peer_free.argtypes = [C.c_void_p]
         _lib = lib
     return _lib
 

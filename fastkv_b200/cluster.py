@@ -125,11 +125,13 @@ class FastKVCluster:
     def _update_kv_sharded(self, key_states, query_states, value_states, k_dst=None, v_dst=None):
         """KV-head-sharded TSP layer: local compress, exchange per-head scores, identical global top-k."""
         w = self.window_size
+        # (p2p exchange: the stores to the peers are enqueued right behind the scoring kernel, before the rank-local
+        # selection and compaction, which do not depend on them — SURVEY.md §8e)
         k, v, _, aux = ops.compress(query_states, key_states, value_states, window_size=w,
                                     kernel_size=self.kernel_size, pooling=self.pooling,
                                     capacity=self.max_capacity_prompt, tsp_len=0, mode=L.MODE_FASTKV,
                                     impl=self.score_impl, return_aux=True, overlap=self.overlap,
-                                    k_out=k_dst, v_out=v_dst)
+                                    k_out=k_dst, v_out=v_dst, after_score=self.shard.begin_exchange)
         tsp, imp = self.shard.global_tsp(aux["score"], self.tsp_length - w, w)
         if self.keep_aux:
             aux["importance"] = imp

@@ -163,6 +163,7 @@ const char* fkv_strerror(int code) {
     case FKV_EMODE: return "unknown or unsupported mode / impl";
     case FKV_EWINDOW: return "window_size out of range (1..64 and < L)";
     case FKV_ERANGE: return "head range outside the selection heads";
+    case FKV_ETIMEOUT: return "a peer never arrived at the score exchange";
   }
   return "unknown fastkv_b200 error";
 }
@@ -282,6 +283,69 @@ int fkv_gather_rows(const fkv_gather_rows_params* p, void* stream) {
     return FKV_EALIGN;
   if (p->pos_in && !p->pos_out) return FKV_EINVAL;
   return launch_gather_rows(*p, (cudaStream_t)stream);
+}
+
+static int check_exchange(const fkv_exchange_params* p) {
+  if (!p || p->struct_size != sizeof(fkv_exchange_params)) return FKV_EINVAL;
+  if (p->world < 1 || p->world > FKV_MAX_PEERS || p->rank < 0 || p->rank >= p->world) return FKV_EINVAL;
+  if (p->B < 1 || p->heads_local < 1 || p->P < 1 || !p->score) return FKV_EINVAL;
+  for (int r = 0; r < p->world; ++r) {
+    if (!p->region[r]) return FKV_EINVAL;
+    if (!aligned16(p->region[r])) return FKV_EALIGN;
+  }
+  const size_t need = (size_t)FKV_EXCHANGE_HEADER_BYTES + (size_t)p->B * p->world * p->heads_local * (size_t)p->P * 4;
+  if (p->region_bytes < need) return FKV_EWORKSPACE;
+  return FKV_OK;
+}
+
+int fkv_exchange_push(const fkv_exchange_params* p, void* stream) {
+  if (int rc = check_exchange(p)) return rc;
+  return launch_exchange_push(*p, (cudaStream_t)stream);
+}
+
+int fkv_exchange_wait(const fkv_exchange_params* p, void* stream) {
+  if (int rc = check_exchange(p)) return rc;
+  return launch_exchange_wait(*p, (cudaStream_t)stream);
+}
+
+int fkv_exchange_status(const void* local_region, void* stream) {
+  if (!local_region) return FKV_EINVAL;
+  return exchange_status(local_region, (cudaStream_t)stream);
+}
+
+int fkv_peer_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t");
+  if (!bytes || !ptr_out || !handle_out) return FKV_EINVAL;
+  void* ptr = nullptr;
+  FKV_CUDA_TRY(cudaMalloc(&ptr, bytes));
+  cudaError_t e = cudaMemset(ptr, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, ptr);
+  if (e != cudaSuccess) { cudaFree(ptr); return (int)e; }
+  memcpy(handle_out, &h, 64);
+  *ptr_out = ptr;
+  return FKV_OK;
+}
+
+int fkv_peer_open(const unsigned char handle[64], void** ptr_out) {
+  if (!handle || !ptr_out) return FKV_EINVAL;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  FKV_CUDA_TRY(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return FKV_OK;
+}
+
+int fkv_peer_close(void* mapped_ptr) {
+  if (!mapped_ptr) return FKV_EINVAL;
+  FKV_CUDA_TRY(cudaIpcCloseMemHandle(mapped_ptr));
+  return FKV_OK;
+}
+
+int fkv_peer_free(void* ptr) {
+  if (!ptr) return FKV_EINVAL;
+  FKV_CUDA_TRY(cudaFree(ptr));
+  return FKV_OK;
 }
 
 int fkv_decode_attn(const fkv_decode_attn_params* p, void* stream) {

@@ -175,4 +175,8 @@ int launch_gather_rows(const fkv_gather_rows_params& p, cudaStream_t s);
 int launch_decode_attn(const fkv_decode_attn_params& p, cudaStream_t s);
 int launch_cache_append(const fkv_cache_append_params& p, cudaStream_t s);
 size_t decode_workspace_bytes(int B, int Hq, int D, int max_seq_len);
+// exchange.cu: the TSP layer's score exchange over peer memory
+int launch_exchange_push(const fkv_exchange_params& p, cudaStream_t s);
+int launch_exchange_wait(const fkv_exchange_params& p, cudaStream_t s);
+int exchange_status(const void* region, cudaStream_t s);
 }  // namespace fkv

@@ -1,0 +1,205 @@
+// The TSP layer's one exchange, written over peer memory instead of a library collective:
+// KV-head-sharded ranks store their per-head score rows straight into each other's HBM (NVLink / NVSwitch P2P
+// stores) so that every rank can sum ALL heads before its global top-k (baselines/fastkv/utils.py:127).
+//
+//   exchange_push_kernel   handshake ("my region may be overwritten") -> 16-byte stores of the local rows into
+//                          every rank's region -> one release of a per-source DATA flag per peer
+//   exchange_wait_kernel   acquires the peers' DATA flags; the consumer (fkv_topk, nsum = all heads) follows on
+//                          the same stream
+// Everything is stream-ordered device work: capturable in a CUDA graph, no host round trip, no NCCL.
+//
+// Region header (u32 words; FKV_EXCHANGE_HEADER_BYTES = 256):
+//   [0]        epoch of the last COMPLETED push of the owner        (owner only)
+//   [1]        departure ticket of the owner's push CTAs           (owner only)
+//   [2]        error word: 1 = a handshake / data wait timed out    (owner only)
+//   [8 + s]    READY word written by rank s: "s has entered push number e" (=> s consumed exchange e - 1)
+//   [16 + s]   DATA word written by rank s: "all rows of s for exchange e are in this region"
+// All words only grow (compared as signed differences), so nothing is ever reset and a replayed graph needs no
+// host-side state: the epoch lives in the region.
+#include "common.cuh"
+
+namespace fkv {
+namespace {
+
+constexpr int kXEpoch = 0, kXTicket = 1, kXErr = 2, kXReady = 8, kXData = 16;
+constexpr int kXThreads = 256;
+static_assert(kXData + FKV_MAX_PEERS <= FKV_EXCHANGE_HEADER_BYTES / 4, "exchange header layout");
+
+struct XArgs {
+  const float* score;
+  int64_t sb, sh;                     // element strides of the local rows
+  int B, hl, rank, world;
+  int64_t P;
+  unsigned int* region[FKV_MAX_PEERS];
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void st_peer16(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Spin until *word has reached `e` (signed difference: the words only grow); false on timeout.
+__device__ bool wait_word(const unsigned int* word, unsigned int e, unsigned long long timeout_ns) {
+  if ((int)(ld_acquire_sys(word) - e) >= 0) return true;
+  const unsigned long long t0 = now_ns();
+  for (;;) {
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      if ((int)(ld_acquire_sys(word) - e) >= 0) return true;
+      __nanosleep(40);
+    }
+    if (now_ns() - t0 > timeout_ns) return false;
+  }
+}
+
+__global__ void __launch_bounds__(kXThreads)
+exchange_push_kernel(const __grid_constant__ XArgs a) {
+  __shared__ unsigned int* region[FKV_MAX_PEERS];               // (indexing the kernel parameter dynamically would spill it to local memory)
+#pragma unroll
+  for (int r = 0; r < FKV_MAX_PEERS; ++r)
+    if (threadIdx.x == r) region[r] = a.region[r];
+  __syncthreads();
+  unsigned int* mine = region[a.rank];
+  const unsigned int e = ld_relaxed_gpu(mine + kXEpoch) + 1u;    // the last CTA out publishes e once every CTA has read this
+  const int tid = threadIdx.x;
+  // (i) handshake.  Entering push number e proves that this rank's consumer of exchange e - 1 has finished (stream
+  // order), so peers may overwrite this region; they learn it from the READY word.  One CTA tells, every CTA listens.
+  if (blockIdx.x == 0 && tid < a.world && tid != a.rank) st_release_sys(region[tid] + kXReady + a.rank, e);
+  if (tid < a.world && tid != a.rank) {
+    if (!wait_word(mine + kXReady + tid, e, a.timeout_ns)) mine[kXErr] = 1u;
+  }
+  __syncthreads();
+
+  // (ii) the rows.  Each 16-byte chunk is loaded once (L2-resident: the scoring kernel has just written it) and stored
+  // to every rank's region, peers first so that the NVLink stores are in flight while the local one is issued.
+  const int H = a.hl * a.world;
+  const int64_t row_elems = a.P;
+  const bool vec = ((row_elems & 3) == 0) && ((a.sb & 3) == 0) && ((a.sh & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(a.score) & 15) == 0);
+  const int rows = a.B * a.hl;
+  if (vec) {
+    const int64_t chunks_per_row = row_elems >> 2;
+    const int64_t total = (int64_t)rows * chunks_per_row;
+    for (int64_t c0 = (int64_t)blockIdx.x * kXThreads * 4 + tid; c0 < total; c0 += (int64_t)gridDim.x * kXThreads * 4) {
+      float4 v[4];
+      int64_t dst_off[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t c = c0 + (int64_t)u * kXThreads;
+        dst_off[u] = -1;
+        if (c < total) {
+          const int r = (int)(c / chunks_per_row);
+          const int64_t i = (c - (int64_t)r * chunks_per_row) << 2;
+          const int b = r / a.hl, h = r - b * a.hl;
+          v[u] = *reinterpret_cast<const float4*>(a.score + b * a.sb + h * a.sh + i);
+          dst_off[u] = ((int64_t)(b * H + a.rank * a.hl + h)) * row_elems + i;
+        }
+      }
+      for (int pp = 1; pp <= a.world; ++pp) {
+        const int peer = (a.rank + pp) % a.world;              // own region last
+        float* dst = reinterpret_cast<float*>(region[peer] + FKV_EXCHANGE_HEADER_BYTES / 4);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (dst_off[u] >= 0) st_peer16(dst + dst_off[u], v[u]);
+      }
+    }
+  } else {                                                       // odd row lengths / unaligned views: 4-byte stores
+    const int64_t total = (int64_t)rows * row_elems;
+    for (int64_t c = (int64_t)blockIdx.x * kXThreads + tid; c < total; c += (int64_t)gridDim.x * kXThreads) {
+      const int r = (int)(c / row_elems);
+      const int64_t i = c - (int64_t)r * row_elems;
+      const int b = r / a.hl, h = r - b * a.hl;
+      const float val = a.score[b * a.sb + h * a.sh + i];
+      const int64_t off = ((int64_t)(b * H + a.rank * a.hl + h)) * row_elems + i;
+      for (int pp = 1; pp <= a.world; ++pp) {
+        const int peer = (a.rank + pp) % a.world;
+        reinterpret_cast<float*>(region[peer] + FKV_EXCHANGE_HEADER_BYTES / 4)[off] = val;
+      }
+    }
+  }
+
+  // (iii) publish.  Every thread orders its stores at system scope, the CTA's ticket is taken after all of them, and
+  // the last CTA out (which has observed every ticket) releases the DATA word in every peer's region.
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(mine + kXTicket, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      mine[kXTicket] = 0u;
+      for (int peer = 0; peer < a.world; ++peer)
+        if (peer != a.rank) st_release_sys(region[peer] + kXData + a.rank, e);
+      st_release_sys(mine + kXEpoch, e);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32)
+exchange_wait_kernel(const __grid_constant__ XArgs a) {
+  unsigned int* mine = nullptr;
+#pragma unroll
+  for (int r = 0; r < FKV_MAX_PEERS; ++r)
+    if (a.rank == r) mine = a.region[r];
+  const unsigned int e = ld_acquire_sys(mine + kXEpoch);        // the push in front of this kernel has completed
+  const int tid = threadIdx.x;
+  if (tid < a.world && tid != a.rank) {
+    if (!wait_word(mine + kXData + tid, e, a.timeout_ns)) mine[kXErr] = 1u;
+  }
+}
+
+XArgs make_args(const fkv_exchange_params& p) {
+  XArgs a{};
+  a.score = p.score; a.sb = p.score_stride_b; a.sh = p.score_stride_h;
+  a.B = p.B; a.hl = p.heads_local; a.rank = p.rank; a.world = p.world; a.P = p.P;
+  for (int r = 0; r < p.world; ++r) a.region[r] = static_cast<unsigned int*>(p.region[r]);
+  a.timeout_ns = (unsigned long long)(p.timeout_ms > 0 ? p.timeout_ms : 20000) * 1000000ull;
+  return a;
+}
+
+}  // namespace
+
+int launch_exchange_push(const fkv_exchange_params& p, cudaStream_t s) {
+  const XArgs a = make_args(p);
+  const int64_t chunks = ((int64_t)p.B * p.heads_local * p.P + 3) / 4;
+  int64_t want = (chunks + kXThreads * 4 - 1) / (kXThreads * 4);
+  int cap = p.max_ctas > 0 ? p.max_ctas : 64;                    // a few dozen SMs saturate the NVLink egress; the rest keep scoring
+  if (cap > num_sms()) cap = num_sms();
+  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  exchange_push_kernel<<<grid, kXThreads, 0, s>>>(a);
+  FKV_LAUNCH_CHECK();
+  return FKV_OK;
+}
+
+int launch_exchange_wait(const fkv_exchange_params& p, cudaStream_t s) {
+  const XArgs a = make_args(p);
+  exchange_wait_kernel<<<1, 32, 0, s>>>(a);
+  FKV_LAUNCH_CHECK();
+  return FKV_OK;
+}
+
+int exchange_status(const void* region, cudaStream_t s) {
+  unsigned int words[4] = {0, 0, 0, 0};
+  FKV_CUDA_TRY(cudaMemcpyAsync(words, region, sizeof(words), cudaMemcpyDeviceToHost, s));
+  FKV_CUDA_TRY(cudaStreamSynchronize(s));
+  return words[kXErr] ? FKV_ETIMEOUT : FKV_OK;
+}
+
+}  // namespace fkv

@@ -6,8 +6,11 @@ selects and compacts only those, and the TSP layer exchanges the per-head score 
 that every rank runs the *same* global top-k (baselines/fastkv/utils.py:127 needs the sum over
 ALL heads).
 
-Two exchange modes:
-  * ``"gather"`` (default) — all-gather the fp32 per-KV-head scores ([B, Hkv/N, P] per rank, 4 MiB
+Three exchange modes:
+  * ``"p2p"`` — the library's own exchange over peer memory (fkv_exchange_push / fkv_exchange_wait): every rank
+    stores its rows straight into the other ranks' HBM over NVLink / NVSwitch, flags instead of a collective,
+    capturable in a CUDA graph.  Same gathered layout and therefore the same bit-identical selection as "gather".
+  * ``"gather"`` (default when no peer memory is available) — all-gather the fp32 per-KV-head scores ([B, Hkv/N, P] per rank, 4 MiB
     total at 128k) and sum them in fixed head order inside the top-k kernel: bit-identical
     selection at every GPU count, identical to the single-GPU result.
   * ``"reduce"`` — one fp32 sum all-reduce of the rank-local partial importance [B, P]
@@ -36,18 +39,40 @@ def head_range(num_heads: int, rank: int, world_size: int) -> Tuple[int, int]:
 class HeadShard:
     """Process-group handle attached to ``FastKVCluster.shard`` on KV-head-sharded runs."""
 
-    def __init__(self, group: Optional[dist.ProcessGroup] = None, exchange: str = "gather"):
-        if exchange not in ("gather", "reduce"):
-            raise ValueError("exchange must be 'gather' or 'reduce'")
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, exchange: str = "gather", region=None):
+        if exchange not in ("gather", "reduce", "p2p"):
+            raise ValueError("exchange must be 'p2p', 'gather' or 'reduce'")
         self.group = group
         self.exchange = exchange
-        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.region = region                      # PeerRegion of the p2p exchange (allocated on first use when None)
+        self.pending = None
+        if region is not None:
+            self.world_size, self.rank = region.world_size, region.rank
+        else:
+            self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+            self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
     def local_heads(self, num_heads: int) -> Tuple[int, int]:
         return head_range(num_heads, self.rank, self.world_size)
 
     # -- the exchange -----------------------------------------------------------------------------
+    def begin_exchange(self, score_local: torch.Tensor) -> None:
+        """p2p only: enqueue the stores of this rank's rows right behind the scoring kernel, so that they travel while
+        the rank-local selection and compaction run; ``exchange_scores`` of the same tensor then only waits."""
+        if self.exchange != "p2p" or self.world_size == 1:
+            return
+        from .peer import PeerRegion
+        b, hl, p = score_local.shape
+        need = PeerRegion.bytes_for(b, hl * self.world_size, p)
+        if self.region is None or self.region.nbytes < need:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("fastkv_b200: the peer region must be allocated before CUDA-graph capture (run one eager step first)")
+            if self.region is not None:
+                self.region.close()
+            self.region = PeerRegion(max(need, 4 << 20), self.group)     # collective: every rank reaches this with the same sizes
+        self.region.push(score_local)
+        self.pending = score_local
+
     def exchange_scores(self, score_local: torch.Tensor, partial: Optional[torch.Tensor] = None) -> torch.Tensor:
         """[B, Hl, P] rank-local scores -> what the global top-k consumes.
 
@@ -57,6 +82,11 @@ class HeadShard:
         if n == 1:
             return score_local
         b, hl, p = score_local.shape
+        if self.exchange == "p2p":
+            if self.pending is not score_local:
+                self.begin_exchange(score_local)
+            self.pending = None
+            return self.region.wait()
         if self.exchange == "gather":
             flat = torch.empty((n * b, hl, p), dtype=score_local.dtype, device=score_local.device)
             dist.all_gather_into_tensor(flat, score_local.contiguous(), group=self.group)   # rank-major concat on dim 0

@@ -210,7 +210,7 @@ def gather_rows(hidden: torch.Tensor, idx: torch.Tensor, position_ids: Optional[
 
 
 def _compress_overlapped(lib, ov, mode, q, k, v, W, kernel_size, pooling, capacity, h0, h1, impl, ws, score_buf, idx,
-                         k_out, v_out, tsp, imp, tsp_k):
+                         k_out, v_out, tsp, imp, tsp_k, after_score=None):
     """score on the current stream, select + compact on the side stream, TSP top-k on the current stream."""
     dev = q.device
     B, Hq, Lq, D = q.shape
@@ -229,6 +229,8 @@ def _compress_overlapped(lib, ov, mode, q, k, v, W, kernel_size, pooling, capaci
     sp.max_ctas = ov.score_ctas
     have_hist = int(sp.hist_slot != 0 and lib.fkv_score_impl_name(C.byref(sp)) == b"tensor")
     L.check(lib.fkv_score(C.byref(sp), main.cuda_stream))
+    if after_score is not None:
+        after_score(score_buf)
     fork = torch.cuda.Event()
     fork.record(main)
     ov.side.wait_event(fork)
@@ -315,14 +317,16 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
              pooling: str, capacity: int, tsp_len: int = 0, mode: int = L.MODE_FASTKV,
              head_range: Optional[Tuple[int, int]] = None, impl: int = L.IMPL_AUTO,
              k_out: Optional[torch.Tensor] = None, v_out: Optional[torch.Tensor] = None,
-             return_aux: bool = False, overlap: Optional[SelectOverlap] = None):
+             return_aux: bool = False, overlap: Optional[SelectOverlap] = None, after_score=None):
     """The fused update_kv chain: score -> per-head top-k -> KV compaction [-> TSP top-k].
 
     Returns (k_out [B,Hsel,C,D], v_out, tsp_idx [B,T] | None) and, with ``return_aux``, a dict with
     the scores [B,Hsel,P], per-head indices [B,Hsel,C-W] and (TSP) importance [B,P].
 
     ``overlap``: run the select + compact stage on the overlap object's side stream (k_out / v_out / idx are then
-    complete only after ``overlap.join()``); the scores and the TSP indices stay on the current stream."""
+    complete only after ``overlap.join()``); the scores and the TSP indices stay on the current stream.
+    ``after_score(score)``: called once the scoring kernel is enqueued (on the overlapped path: before the select
+    stage is; otherwise after the whole chain) — the hook the multi-GPU score exchange starts from."""
     L.require_cuda(q, k)
     L.require_cuda_or_pinned(v)
     lib = L.load()
@@ -349,7 +353,7 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
     ws = L.workspace(dev, lib.fkv_workspace_bytes(mode, B, Hq, Hkv, Lq, W, capacity, tsp_k))
     if overlap is not None and v.is_cuda and B * Hsel <= L.SELECT_MAX_ROWS and 1 <= capacity - W <= 2048 and capacity - W <= P:
         _compress_overlapped(lib, overlap, mode, q, k, v, W, kernel_size, pooling, capacity, h0, h1, impl, ws, score_buf, idx,
-                             k_out, v_out, tsp, imp, tsp_k)
+                             k_out, v_out, tsp, imp, tsp_k, after_score)
         if return_aux:
             return k_out, v_out, tsp, dict(score=score_buf, idx=idx, importance=imp)
         return k_out, v_out, tsp
@@ -363,6 +367,8 @@ def compress(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, window_size: 
     p.tsp_out = tsp.data_ptr() if tsp is not None else None
     p.imp_out = imp.data_ptr() if imp is not None else None
     L.check(lib.fkv_compress(C.byref(p), L.stream_ptr(dev)))
+    if after_score is not None:
+        after_score(score_buf)
     if return_aux:
         return k_out, v_out, tsp, dict(score=score_buf, idx=idx, importance=imp)
     return k_out, v_out, tsp

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FKV_ABI_VERSION 4
+#define FKV_ABI_VERSION 5
 
 /* Every `workspace` argument below is one kind of buffer: device memory, 256-byte aligned, passed ONCE through
  * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state owned by the library: 256 bytes
@@ -53,7 +53,8 @@ enum {
   FKV_EWORKSPACE = -7,  /* workspace missing or smaller than fkv_workspace_bytes()                 */
   FKV_EMODE = -8,       /* unknown mode / impl, or combination not supported                       */
   FKV_EWINDOW = -9,     /* window_size < 1, > 64, or >= L                                          */
-  FKV_ERANGE = -10      /* head range [h0,h1) outside the selection heads                          */
+  FKV_ERANGE = -10,     /* head range [h0,h1) outside the selection heads                          */
+  FKV_ETIMEOUT = -11    /* a peer never showed up in fkv_exchange_push / _wait (fkv_exchange_status) */
 };
 
 /* ---- tensor view ------------------------------------------------------------------------- */
@@ -253,6 +254,52 @@ typedef struct fkv_compress_params {
 } fkv_compress_params;
 
 int fkv_compress(const fkv_compress_params* p, void* stream);
+
+/* ---- the TSP layer's score exchange over peer memory (multi-GPU, KV heads sharded over the ranks) -------------- */
+/* baselines/fastkv/utils.py:127 sums the scores of ALL kv heads before the TSP top-k, so KV-head-sharded ranks must
+ * see each other's [B, heads_local, P] fp32 score rows once per prefill.  Instead of a library all-gather, every
+ * rank owns one PEER REGION (device memory mapped into every rank of the box: CUDA IPC or a torch symmetric-memory
+ * allocation, NVLink / NVSwitch underneath) and the ranks store their rows straight into each other's regions:
+ *
+ *   region = [FKV_EXCHANGE_HEADER_BYTES of flags and counters, zero-initialised once]
+ *            [gathered scores: fp32 [B][world * heads_local][P], head-major, the layout fkv_topk sums with nsum]
+ *
+ * fkv_exchange_push  (i) tells every peer "my previous TSP top-k is done, my region may be overwritten" and waits for
+ *                    the same word from every peer, (ii) stores the local rows into every rank's region (its own
+ *                    included) with 16-byte stores, (iii) releases a per-source DATA flag in every region.
+ * fkv_exchange_wait  one small CTA that acquires the DATA flags of all peers; kernels enqueued behind it on the same
+ *                    stream (fkv_topk with src = region + FKV_EXCHANGE_HEADER_BYTES, nsum = world * heads_local)
+ *                    read the complete gathered rows.
+ * Both only enqueue kernels (CUDA-graph capturable, no host synchronisation, no NCCL); work that does not depend on
+ * the exchange (the rank-local per-head selection and compaction) can be enqueued between the two.  One exchange may
+ * be in flight per region; push / wait / consumer must be enqueued on ONE stream per rank, in that order, and every
+ * rank must issue the same sequence of exchanges.  A wait that sees no peer for `timeout_ms` (default 20 000) gives
+ * up, records it in the region (fkv_exchange_status) and lets the stream continue rather than hang the GPU.        */
+#define FKV_MAX_PEERS 8
+#define FKV_EXCHANGE_HEADER_BYTES 256
+typedef struct fkv_exchange_params {
+  uint32_t struct_size;
+  int32_t rank, world;                /* world <= FKV_MAX_PEERS                                              */
+  int32_t B, heads_local;             /* local rows: [B, heads_local, P]                                     */
+  int64_t P;
+  const float* score;                 /* local scores (device); element strides below, P contiguous          */
+  int64_t score_stride_b, score_stride_h;
+  void* region[FKV_MAX_PEERS];        /* region[r] = rank r's peer region AS MAPPED IN THIS PROCESS          */
+  size_t region_bytes;                /* >= FKV_EXCHANGE_HEADER_BYTES + B * world * heads_local * P * 4      */
+  int32_t max_ctas;                   /* 0 = library default                                                  */
+  int32_t timeout_ms;                 /* 0 = 20 000                                                           */
+} fkv_exchange_params;
+int fkv_exchange_push(const fkv_exchange_params* p, void* stream);
+int fkv_exchange_wait(const fkv_exchange_params* p, void* stream);
+/* SYNCHRONISES `stream`; FKV_OK, or FKV_ETIMEOUT when a push / wait on this rank's region ever timed out. */
+int fkv_exchange_status(const void* local_region, void* stream);
+/* Set-up helpers for callers without their own peer-memory allocator (these four DO allocate / map and are not
+ * stream-ordered): cudaMalloc + zero + cudaIpcGetMemHandle, cudaIpcOpenMemHandle (enables peer access lazily),
+ * cudaIpcCloseMemHandle, cudaFree.  `handle` is the 64-byte cudaIpcMemHandle_t, to be sent to the other ranks. */
+int fkv_peer_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]);
+int fkv_peer_open(const unsigned char handle[64], void** ptr_out);
+int fkv_peer_close(void* mapped_ptr);
+int fkv_peer_free(void* ptr);
 
 /* ---- queries ----------------------------------------------------------------------------- */
 /* Bytes of scratch fkv_score / fkv_topk / fkv_compress need for these sizes (upper bound).     */

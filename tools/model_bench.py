@@ -77,7 +77,7 @@ def run(args):
     patch.set_model(model, a)
     if tp > 1 and args.method == "fastkv":
         from fastkv_b200.dist import HeadShard
-        shard = HeadShard(exchange="gather")          # the path's one exchange: per-head scores at the TSP layer
+        shard = HeadShard(exchange=os.environ.get("FKV_EXCHANGE", "gather"))   # the path's one exchange: per-head scores at the TSP layer
         for layer in model.model.layers:
             layer.self_attn.kv_cluster.shard = shard
     ids = torch.ones((args.batch, args.ctx), dtype=torch.int64, device="cuda")      # benchmark/e2e.py:55
