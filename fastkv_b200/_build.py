@@ -39,6 +39,8 @@ def build_library(force=False, verbose=False):
     flags = list(NVCC_FLAGS)
     if os.environ.get("FKV_BUILD_TRACE") == "1":      # compile the %globaltimer phase timelines into the scoring kernel
         flags.append("-DFKV_TC_TRACING")
+    if os.environ.get("FKV_BUILD_XTRACE") == "1":     # %globaltimer stamps of the peer-memory exchange (tools/exchange_trace.py)
+        flags.append("-DFKV_X_TRACING")
     cmd = [nvcc] + flags + ["-o", LIB] + sources()
     proc = subprocess.run(cmd, capture_output=True, text=True)
     log = proc.stdout + proc.stderr

@@ -9,21 +9,32 @@
 // Everything is stream-ordered device work: capturable in a CUDA graph, no host round trip, no NCCL.
 //
 // Region header (u32 words; FKV_EXCHANGE_HEADER_BYTES = 256):
-//   [0]        epoch of the last COMPLETED push of the owner        (owner only)
-//   [1]        departure ticket of the owner's push CTAs           (owner only)
-//   [2]        error word: 1 = a handshake / data wait timed out    (owner only)
+//   [0]        number of exchanges completed on the owner (bumped by its wait kernel)             (owner only)
+//   [2]        error word: 1 = a handshake / data wait timed out                                  (owner only)
 //   [8 + s]    READY word written by rank s: "s has entered push number e" (=> s consumed exchange e - 1)
-//   [16 + s]   DATA word written by rank s: "all rows of s for exchange e are in this region"
+//   [16 + s]   DATA counter, bumped once by every push CTA of rank s after its rows are in this region
+//   [24 + s]   DATA count the owner has already consumed from rank s                               (owner only)
 // All words only grow (compared as signed differences), so nothing is ever reset and a replayed graph needs no
-// host-side state: the epoch lives in the region.
+// host-side state: the epoch and the expected counts live in the region.
+//
+// Measured between two B200s (tools/exchange_trace.py, profiles/r2_exchange.md): the first version (per-thread
+// system fences, a last-CTA-out ticket, release stores for every flag) took 17.5 us for 512 KiB per rank, of which
+// 5 us were CTAs queueing behind each other's remote stores, and 5.5 us three serialised system fences of the last
+// CTA.  Now every CTA publishes its own rows with ONE fence and one remote atomic, and the receiver counts CTAs.
 #include "common.cuh"
 
 namespace fkv {
 namespace {
 
-constexpr int kXEpoch = 0, kXTicket = 1, kXErr = 2, kXReady = 8, kXData = 16;
+constexpr int kXEpoch = 0, kXErr = 2, kXReady = 8, kXData = 16, kXSeen = 24;
+constexpr int kXTrace = 32;           // u64[16] %globaltimer stamps of the last exchange (FKV_X_TRACING builds only)
+#ifdef FKV_X_TRACING
+#define FKV_XT(i) reinterpret_cast<unsigned long long*>(mine + kXTrace)[i] = now_ns()
+#else
+#define FKV_XT(i)
+#endif
 constexpr int kXThreads = 256;
-static_assert(kXData + FKV_MAX_PEERS <= FKV_EXCHANGE_HEADER_BYTES / 4, "exchange header layout");
+static_assert(kXSeen + FKV_MAX_PEERS <= 32 && FKV_MAX_PEERS == 8, "exchange header layout");
 
 struct XArgs {
   const float* score;
@@ -32,6 +43,7 @@ struct XArgs {
   int64_t P;
   unsigned int* region[FKV_MAX_PEERS];
   unsigned long long timeout_ns;
+  unsigned int push_ctas;             // grid of the push kernel: what every receiver adds to its expected DATA count
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
@@ -42,6 +54,18 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned int ld_relaxed_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_relaxed_sys(unsigned int* p, unsigned int v) {
+  asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -56,15 +80,16 @@ __device__ __forceinline__ void st_peer16(float* p, const float4& v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-// Spin until *word has reached `e` (signed difference: the words only grow); false on timeout.
+// Spin until *word has reached `e` (signed difference: the words only grow); false on timeout.  Relaxed polls: the
+// caller fences once after the wait where it needs acquire semantics.
 __device__ bool wait_word(const unsigned int* word, unsigned int e, unsigned long long timeout_ns) {
-  if ((int)(ld_acquire_sys(word) - e) >= 0) return true;
+  if ((int)(ld_relaxed_sys(word) - e) >= 0) return true;
   const unsigned long long t0 = now_ns();
   for (;;) {
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
-      if ((int)(ld_acquire_sys(word) - e) >= 0) return true;
-      __nanosleep(40);
+      if ((int)(ld_relaxed_sys(word) - e) >= 0) return true;
+      __nanosleep(20);
     }
     if (now_ns() - t0 > timeout_ns) return false;
   }
@@ -78,15 +103,18 @@ exchange_push_kernel(const __grid_constant__ XArgs a) {
     if (threadIdx.x == r) region[r] = a.region[r];
   __syncthreads();
   unsigned int* mine = region[a.rank];
-  const unsigned int e = ld_relaxed_gpu(mine + kXEpoch) + 1u;    // the last CTA out publishes e once every CTA has read this
+  const unsigned int e = ld_relaxed_gpu(mine + kXEpoch) + 1u;    // bumped by this rank's wait kernel, i.e. after every CTA here
   const int tid = threadIdx.x;
+  if (blockIdx.x == 0 && tid == 0) FKV_XT(0);
   // (i) handshake.  Entering push number e proves that this rank's consumer of exchange e - 1 has finished (stream
   // order), so peers may overwrite this region; they learn it from the READY word.  One CTA tells, every CTA listens.
-  if (blockIdx.x == 0 && tid < a.world && tid != a.rank) st_release_sys(region[tid] + kXReady + a.rank, e);
+  // Nothing is published by READY (the reads it reports are complete by the kernel boundary): relaxed accesses.
+  if (blockIdx.x == 0 && tid < a.world && tid != a.rank) st_relaxed_sys(region[tid] + kXReady + a.rank, e);
   if (tid < a.world && tid != a.rank) {
     if (!wait_word(mine + kXReady + tid, e, a.timeout_ns)) mine[kXErr] = 1u;
   }
   __syncthreads();
+  if (blockIdx.x == 0 && tid == 0) FKV_XT(1);
 
   // (ii) the rows.  Each 16-byte chunk is loaded once (L2-resident: the scoring kernel has just written it) and stored
   // to every rank's region, peers first so that the NVLink stores are in flight while the local one is issued.
@@ -98,11 +126,11 @@ exchange_push_kernel(const __grid_constant__ XArgs a) {
   if (vec) {
     const int64_t chunks_per_row = row_elems >> 2;
     const int64_t total = (int64_t)rows * chunks_per_row;
-    for (int64_t c0 = (int64_t)blockIdx.x * kXThreads * 4 + tid; c0 < total; c0 += (int64_t)gridDim.x * kXThreads * 4) {
-      float4 v[4];
-      int64_t dst_off[4];
+    for (int64_t c0 = (int64_t)blockIdx.x * kXThreads * 2 + tid; c0 < total; c0 += (int64_t)gridDim.x * kXThreads * 2) {
+      float4 v[2];
+      int64_t dst_off[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int64_t c = c0 + (int64_t)u * kXThreads;
         dst_off[u] = -1;
         if (c < total) {
@@ -117,7 +145,7 @@ exchange_push_kernel(const __grid_constant__ XArgs a) {
         const int peer = (a.rank + pp) % a.world;              // own region last
         float* dst = reinterpret_cast<float*>(region[peer] + FKV_EXCHANGE_HEADER_BYTES / 4);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 2; ++u)
           if (dst_off[u] >= 0) st_peer16(dst + dst_off[u], v[u]);
       }
     }
@@ -135,21 +163,16 @@ exchange_push_kernel(const __grid_constant__ XArgs a) {
       }
     }
   }
+  if (blockIdx.x == 0 && tid == 0) FKV_XT(2);
 
-  // (iii) publish.  Every thread orders its stores at system scope, the CTA's ticket is taken after all of them, and
-  // the last CTA out (which has observed every ticket) releases the DATA word in every peer's region.
-  __threadfence_system();
+  // (iii) publish, per CTA: the CTA barrier orders every thread's stores before the ONE system-scope fence of the
+  // thread that then bumps the DATA counter in each peer's region (a remote atomic: the receiver counts CTAs).
   __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(mine + kXTicket, 1u);
-    if (prev == gridDim.x - 1) {
-      __threadfence_system();
-      mine[kXTicket] = 0u;
-      for (int peer = 0; peer < a.world; ++peer)
-        if (peer != a.rank) st_release_sys(region[peer] + kXData + a.rank, e);
-      st_release_sys(mine + kXEpoch, e);
-    }
+  if (tid < a.world && tid != a.rank) {
+    fence_sys();
+    red_add_relaxed_sys(region[tid] + kXData + a.rank, 1u);
   }
+  if (blockIdx.x == 0 && tid == 0) FKV_XT(3);
 }
 
 __global__ void __launch_bounds__(32)
@@ -158,11 +181,28 @@ exchange_wait_kernel(const __grid_constant__ XArgs a) {
 #pragma unroll
   for (int r = 0; r < FKV_MAX_PEERS; ++r)
     if (a.rank == r) mine = a.region[r];
-  const unsigned int e = ld_acquire_sys(mine + kXEpoch);        // the push in front of this kernel has completed
   const int tid = threadIdx.x;
+  if (tid == 0) FKV_XT(6);
   if (tid < a.world && tid != a.rank) {
-    if (!wait_word(mine + kXData + tid, e, a.timeout_ns)) mine[kXErr] = 1u;
+    const unsigned int want = mine[kXSeen + tid] + a.push_ctas;  // every rank pushes the same shape with the same grid
+    if (!wait_word(mine + kXData + tid, want, a.timeout_ns)) mine[kXErr] = 1u;
+    mine[kXSeen + tid] = want;
   }
+  fence_sys();                                                   // acquire: the rows behind the counters (the kernel boundary that follows orders the consumer)
+  __syncwarp();
+  if (tid == 0) {
+    mine[kXEpoch] = mine[kXEpoch] + 1u;                          // the push in front of this kernel has completed: stream order
+    FKV_XT(7);
+  }
+}
+
+int push_grid(const fkv_exchange_params& p) {
+  const int64_t chunks = ((int64_t)p.B * p.heads_local * p.P + 3) / 4;
+  const int64_t want = (chunks + kXThreads - 1) / kXThreads;     // one 16-byte chunk per thread until the cap
+  static const int env_cap = getenv("FKV_X_CTAS") ? atoi(getenv("FKV_X_CTAS")) : 0;   // tuning aid; must agree on all ranks
+  int cap = p.max_ctas > 0 ? p.max_ctas : (env_cap > 0 ? env_cap : 128);   // remote stores drain slowly per SM: spread them over most of the chip
+  if (cap > num_sms()) cap = num_sms();
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
 XArgs make_args(const fkv_exchange_params& p) {
@@ -171,6 +211,7 @@ XArgs make_args(const fkv_exchange_params& p) {
   a.B = p.B; a.hl = p.heads_local; a.rank = p.rank; a.world = p.world; a.P = p.P;
   for (int r = 0; r < p.world; ++r) a.region[r] = static_cast<unsigned int*>(p.region[r]);
   a.timeout_ns = (unsigned long long)(p.timeout_ms > 0 ? p.timeout_ms : 20000) * 1000000ull;
+  a.push_ctas = (unsigned)push_grid(p);
   return a;
 }
 
@@ -178,12 +219,7 @@ XArgs make_args(const fkv_exchange_params& p) {
 
 int launch_exchange_push(const fkv_exchange_params& p, cudaStream_t s) {
   const XArgs a = make_args(p);
-  const int64_t chunks = ((int64_t)p.B * p.heads_local * p.P + 3) / 4;
-  int64_t want = (chunks + kXThreads * 4 - 1) / (kXThreads * 4);
-  int cap = p.max_ctas > 0 ? p.max_ctas : 64;                    // a few dozen SMs saturate the NVLink egress; the rest keep scoring
-  if (cap > num_sms()) cap = num_sms();
-  const int grid = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  exchange_push_kernel<<<grid, kXThreads, 0, s>>>(a);
+  exchange_push_kernel<<<a.push_ctas, kXThreads, 0, s>>>(a);
   FKV_LAUNCH_CHECK();
   return FKV_OK;
 }
