@@ -40,11 +40,16 @@ class FastKVCluster:
         self.keep_aux = False                   # keep scores / indices of the last call in self.last_aux
         self.last_aux = None
         # optional callable (batch, kv_heads, rows, head_dim, dtype, device) -> (k_buf, v_buf) [B,Hkv,rows,D] views:
-        # the compaction kernel then writes straight into the caller's cache slot
+        # the compaction kernel then writes straight into the caller's cache slot.  Calls on HOST
+        # tensors ask with device = cpu: the compact K/V are then copied into the returned (pinned) host buffers instead of
+        # freshly allocated ones (None = allocate)
         self.out_provider = None
         # optional ops.SelectOverlap: the select + compact stage runs on its side stream and the returned K/V are
         # complete only after overlap.join() (the model glue joins at the end of the prefill, bench.py at the end of a step)
         self.overlap = None
+        # optional ops.HostPipeline: calls on pinned HOST tensors run on its streams round-robin and return without
+        # synchronising (results complete after host_pipeline.join()); None = every host call blocks until its results landed
+        self.host_pipeline = None
 
     def reset(self, window_size=8, max_capacity_prompt=512, kernel_size=7, pooling='avgpool', tsp_layer=False,
               tsp_length=2048, tsp_rate=0.25, retain_rate=0.25, eviction_mode="constant"):
@@ -82,6 +87,14 @@ class FastKVCluster:
         want_tsp = bool(self.tsp_layer and q_len > self.tsp_length)
 
         host_io = not key_states.is_cuda
+        if host_io and self.host_pipeline is not None and key_states.is_pinned():
+            with torch.cuda.stream(self.host_pipeline.next_stream()):
+                return self._update_kv_impl(key_states, query_states, value_states, num_key_value_groups, want_tsp, blocking=False)
+        return self._update_kv_impl(key_states, query_states, value_states, num_key_value_groups, want_tsp, blocking=True)
+
+    def _update_kv_impl(self, key_states, query_states, value_states, num_key_value_groups, want_tsp, blocking):
+        bsz, num_heads, q_len, head_dim = query_states.shape
+        host_io = not key_states.is_cuda
         if host_io:
             if not torch.cuda.is_available():
                 raise RuntimeError("fastkv_b200 has no CPU path: a CUDA device is required")
@@ -117,9 +130,18 @@ class FastKVCluster:
             if self.keep_aux:
                 self.last_aux = res[3]
         if host_io:
-            k, v = _to_pinned_host(k), _to_pinned_host(v)
+            dst = None
+            if self.out_provider is not None:          # the caller's own (pinned) host cache slot for this layer
+                dst = self.out_provider(bsz, k.shape[1], k.shape[2], head_dim, k.dtype, torch.device("cpu"))
+            if dst is not None:
+                dst[0].copy_(k, non_blocking=True)
+                dst[1].copy_(v, non_blocking=True)
+                k, v = dst
+            else:
+                k, v = _to_pinned_host(k), _to_pinned_host(v)
             tsp = _to_pinned_host(tsp) if tsp is not None else None
-            torch.cuda.current_stream().synchronize()      # results are on the host when we return
+            if blocking:
+                torch.cuda.current_stream().synchronize()  # results are on the host when we return
         return k, v, tsp
 
     def _update_kv_sharded(self, key_states, query_states, value_states, k_dst=None, v_dst=None):

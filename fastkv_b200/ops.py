@@ -57,6 +57,35 @@ class SelectOverlap:
         self._keep.clear()
 
 
+class HostPipeline:
+    """Round-robin CUDA streams for ``update_kv`` calls whose inputs live in pinned HOST memory.
+
+    A blocking host call is H2D(K) -> kernels -> D2H(compact K/V) -> synchronize: the bus idles in one direction at
+    any time and entirely while the host waits.  With a pipeline attached (``FastKVCluster.host_pipeline``) call i
+    runs on stream i mod depth and returns WITHOUT synchronising, torch's ``non_blocking=True`` contract: the returned
+    pinned tensors are complete after ``join()``.  The H2D copy of call i + 1 then overlaps the kernels and the D2H
+    copy of call i (PCIe is full duplex, the GPU has separate copy engines per direction)."""
+
+    def __init__(self, device=None, depth: int = 2):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, depth))]
+        self.calls = 0
+
+    def next_stream(self) -> torch.cuda.Stream:
+        s = self.streams[self.calls % len(self.streams)]
+        self.calls += 1
+        return s
+
+    def last_stream(self) -> torch.cuda.Stream:
+        """The stream of the most recent call: work enqueued on it is ordered behind that call's results."""
+        return self.streams[(self.calls - 1) % len(self.streams)]
+
+    def join(self) -> None:
+        """Block the host until every call issued so far has delivered its results."""
+        for s in self.streams:
+            s.synchronize()
+
+
 def _score_params(mode, q, k, window_size, kernel_size, pooling, score, h0, h1, qh0, qh1, impl, ws):
     B, Hq, Lq, D = q.shape
     _, Hkv, Lk, Dk = k.shape

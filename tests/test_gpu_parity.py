@@ -682,6 +682,34 @@ def test_host_buffer_path_matches_device_path():
         assert not x.is_cuda and torch.equal(x, y.cpu())
 
 
+def test_pipelined_host_calls_deliver_the_blocking_results():
+    """FastKVCluster.host_pipeline: calls on pinned host tensors return without synchronising (round-robin streams);
+    after join() every call's results equal the blocking call's."""
+    from fastkv_b200 import FastKVCluster, ops
+    knobs = dict(window_size=8, max_capacity_prompt=256, kernel_size=7, pooling="avgpool", tsp_layer=True, tsp_length=512)
+    inputs = [[t.pin_memory() for t in make_inputs(30 + i, 1, 32, 8, 4096, 128, layout="bhld")] for i in range(5)]
+    want = [FastKVCluster(**knobs).update_kv(k, q, v, None, 4, 0) for (q, k, v) in inputs]
+    pipe = ops.HostPipeline(DEV, depth=2)
+    cl = FastKVCluster(**knobs)
+    cl.host_pipeline = pipe
+    got = [cl.update_kv(k, q, v, None, 4, 0) for (q, k, v) in inputs]
+    pipe.join()
+    for a, b in zip(got, want):
+        for x, y in zip(a, b):
+            assert not x.is_cuda and x.is_pinned() and torch.equal(x, y)
+    # results delivered into the caller's own pinned host cache slots (out_provider asked with device = cpu)
+    slots = [tuple(torch.empty((1, 8, 256, 128), dtype=torch.bfloat16, pin_memory=True) for _ in range(2)) for _ in inputs]
+    got = []
+    for i, (q, k, v) in enumerate(inputs):
+        cl.out_provider = lambda *a, _s=slots[i]: _s
+        got.append(cl.update_kv(k, q, v, None, 4, 0))
+    pipe.join()
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a[0] is slots[i][0] and a[1] is slots[i][1]
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+
+
 def test_gather_kv_reads_pinned_host_sources_zero_copy():
     """K/V gather sources may be page-locked host tensors (only the selected rows cross PCIe); outputs are on the GPU."""
     from fastkv_b200 import ops
