@@ -171,6 +171,7 @@ def _make_forwards(mod, method, sliding_window_attr=False):
         query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin)
 
         self.tsp_idx = None                            # never let a previous call's selection leak into this one
+        self.rows_kept = None                          # set when this call returns attention rows for the TSP-kept tokens only
         decode_native = False
         if past_key_values is not None:
             if q_len > 1:
@@ -219,10 +220,35 @@ def _make_forwards(mod, method, sliding_window_attr=False):
             extra = {}
             if sliding_window_attr:
                 extra["sliding_window"] = getattr(self.config, "sliding_window", None)
-            attn_output, attn_weights = attention_interface(
-                self, query_states, key_states, value_states, attention_mask,
-                dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **extra, **kwargs)
-            attn_output = attn_output.reshape(*input_shape, -1).contiguous()
+            impl = getattr(self.config, "_attn_implementation", None) or "eager"
+            if (self.tsp_idx is not None and q_len > 1 and impl in ("sdpa", "eager")
+                    and getattr(self.config, "fastkv_sparse_tsp_layer", True)):
+                # only the T kept tokens leave the TSP layer (llama_model.py:252-259 gathers them after
+                # the MLP), and attention / o_proj / MLP rows are independent of each other, so the layer computes just those
+                # rows: T queries over all L keys under the same causal (and sliding-window) rule, in original positions
+                rows = self.tsp_idx                                                # [B,T] ascending original positions
+                b, hq, _, d = query_states.shape
+                t_keep = rows.shape[1]
+                q_sel = query_states.gather(2, rows[:, None, :, None].expand(b, hq, t_keep, d))
+                j = torch.arange(q_len, device=rows.device)[None, None, :]
+                keep = j <= rows[:, :, None]
+                window = extra.get("sliding_window")
+                if window is not None and q_len > window:
+                    keep &= (rows[:, :, None] - j) < window
+                mask = torch.zeros((b, 1, t_keep, q_len), dtype=q_sel.dtype, device=q_sel.device)
+                mask.masked_fill_(~keep[:, None], torch.finfo(q_sel.dtype).min)
+                kw = dict(kwargs)
+                kw["is_causal"] = False
+                attn_output, attn_weights = attention_interface(
+                    self, q_sel, key_states, value_states, mask,
+                    dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **extra, **kw)
+                attn_output = attn_output.reshape(b, t_keep, -1).contiguous()
+                self.rows_kept = rows
+            else:
+                attn_output, attn_weights = attention_interface(
+                    self, query_states, key_states, value_states, attention_mask,
+                    dropout=0.0 if not self.training else self.attention_dropout, scaling=self.scaling, **extra, **kwargs)
+                attn_output = attn_output.reshape(*input_shape, -1).contiguous()
         attn_output = self.o_proj(attn_output)
         return attn_output, attn_weights
 
@@ -233,6 +259,12 @@ def _make_forwards(mod, method, sliding_window_attr=False):
         hidden_states, _ = self.self_attn(
             hidden_states=hidden_states, attention_mask=attention_mask, position_ids=position_ids,
             past_key_values=past_key_values, use_cache=use_cache, position_embeddings=position_embeddings, **kwargs)
+        rows_kept = getattr(self.self_attn, "rows_kept", None)
+        kept_positions = None
+        if rows_kept is not None:
+            # the attention already returned the TSP-kept rows only: gather the residual stream (and the position ids)
+            # here instead of after the MLP; everything below is per token, so the result is the reference's
+            residual, kept_positions = ops.gather_rows(residual, rows_kept, position_ids)
         hidden_states = residual + hidden_states
         residual = hidden_states
         hidden_states = self.post_attention_layernorm(hidden_states)
@@ -242,7 +274,9 @@ def _make_forwards(mod, method, sliding_window_attr=False):
         # [FastKV] select important tokens and adjust position_ids at the TSP layer
         tsp_idx = getattr(self.self_attn, "tsp_idx", None)
         cluster = getattr(self.self_attn, "kv_cluster", None)
-        if cluster is not None and getattr(cluster, "tsp_layer", False) and tsp_idx is not None:
+        if rows_kept is not None:
+            self.new_position_ids = kept_positions
+        elif cluster is not None and getattr(cluster, "tsp_layer", False) and tsp_idx is not None:
             hidden_states, self.new_position_ids = ops.gather_rows(hidden_states, tsp_idx, position_ids)
         else:
             self.new_position_ids = None

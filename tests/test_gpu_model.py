@@ -83,6 +83,34 @@ def test_fp32_prefill_matches_glue_oracle(patched):
     assert out.last_hidden_state.shape == (2, 1, 512)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-4), (torch.bfloat16, 6e-2)])
+def test_tsp_layer_computes_only_the_kept_rows(patched, dtype, tol):
+    """SURVEY.md §8f rank 1: at the TSP layer attention / o_proj / MLP run for the T kept tokens only (default);
+    ``config.fastkv_sparse_tsp_layer = False`` is the reference's order (all L rows, gather after the MLP).  Same
+    selection, same caches up to the TSP layer, same hidden states after it."""
+    ids = torch.randint(0, 211, (2, 900), generator=torch.Generator().manual_seed(11)).to(DEV)
+    outs = []
+    for sparse in (False, True):
+        gm = _model(dtype).to(DEV)
+        gm.config.fastkv_sparse_tsp_layer = sparse
+        for layer in gm.model.layers:
+            layer.self_attn.config.fastkv_sparse_tsp_layer = sparse
+        patched.set_model(gm, _args())
+        with torch.no_grad():
+            out = gm.model(ids, use_cache=True)
+        torch.cuda.synchronize()
+        assert (gm.model.layers[1].self_attn.rows_kept is not None) == sparse
+        assert gm.model.layers[0].self_attn.rows_kept is None and gm.model.layers[2].self_attn.rows_kept is None
+        outs.append((out.last_hidden_state.float().cpu(), gm.model.layers[1].self_attn.tsp_idx.cpu(),
+                     [tuple(t[:, :, :out.past_key_values.buffers(i)[2]].float().cpu() for t in out.past_key_values.buffers(i)[:2])
+                      for i in range(3)]))
+    (h0, t0, c0), (h1, t1, c1) = outs
+    assert torch.equal(t0, t1)
+    for i in range(2):                                  # caches of layers 0 and 1 do not depend on the TSP layer's attention
+        assert torch.equal(c0[i][0], c1[i][0]) and torch.equal(c0[i][1], c1[i][1])
+    assert torch.allclose(h0, h1, atol=tol, rtol=tol)
+
+
 def test_bf16_prefill_and_native_decode(patched):
     """Decode over the compact cache with the K5 kernel agrees with HF attention over the same cache."""
     from fastkv_b200 import ops

@@ -81,6 +81,8 @@ def run(args):
         for layer in model.model.layers:
             layer.self_attn.kv_cluster.shard = shard
     ids = torch.ones((args.batch, args.ctx), dtype=torch.int64, device="cuda")      # benchmark/e2e.py:55
+    if getattr(args, "dense_tsp_layer", False):
+        model.config.fastkv_sparse_tsp_layer = False
     model.config.fastkv_max_new_tokens = args.genlen
     model.model.config.fastkv_max_new_tokens = args.genlen
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
@@ -126,7 +128,7 @@ def run(args):
         "n_gpus": tp, "parallelism": f"tp{tp} (kv-head-sharded compressor, 2 hidden all-reduces per layer)" if tp > 1 else "none",
         "model": args.model, "layers": args.layers or (32 if args.model == "llama" else 36), "method": args.method,
         "ctx": args.ctx, "batch": args.batch, "capacity": args.capacity, "tsp_len": args.tsp_len, "tsp_idx": tsp_idx,
-        "genlen": args.genlen, "decode_cuda_graph": bool(args.graph and args.method != "fullkv" and tp == 1), "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
+        "genlen": args.genlen, "tsp_layer_rows": "all" if getattr(args, "dense_tsp_layer", False) else "kept only", "decode_cuda_graph": bool(args.graph and args.method != "fullkv" and tp == 1), "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
         "decode_tok_s": round(args.batch * (args.genlen - 1) / (dec / 1e3), 1),
         "reference_throughput_tok_s": round((args.genlen - 1) / ((ttft + dec) / 1e3), 2),   # benchmark/e2e.py:183 definition
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2), "data": "random-init weights, all-ones ids",
@@ -154,4 +156,6 @@ if __name__ == "__main__":
     ap.add_argument("--layers", type=int, default=0)
     ap.add_argument("--runs", type=int, default=2)
     ap.add_argument("--graph", action="store_true", help="CUDA-graph the decode step")
+    ap.add_argument("--dense-tsp-layer", action="store_true",
+                    help="the reference's order at the TSP layer: attention / MLP for all L rows, gather afterwards (default: kept rows only)")
     run(ap.parse_args())

@@ -43,5 +43,16 @@ ops.decode_attn(qd, kc, vc, 901)                                                
 ops.decode_attn(qd, kc, vc, 40)                                                     # single CTA per head group
 sl = torch.tensor([901], dtype=torch.int32, device="cuda")
 ops.decode_attn(qd, kc, vc, 0, seq_len_dev=sl)
+# the peer-memory score exchange kernels (one rank: the sanitizer serialises kernels, so ranks that wait for each other on
+# one device cannot run under it; the flag protocol is covered by tests/test_gpu_exchange.py): vector path, scalar path
+from fastkv_b200.peer import PeerRegion
+for (hl, p_) in [(2, 4088), (3, 1021)]:
+    (reg,) = PeerRegion.local_group(1, PeerRegion.bytes_for(2, hl, p_), torch.device("cuda", 0))
+    for it in range(2):
+        src = torch.rand(2, hl, p_, device="cuda")
+        reg.push(src)
+        out = reg.wait()
+        torch.cuda.synchronize()
+        assert torch.equal(out, src) and reg.status() == 0
 torch.cuda.synchronize()
 print("sanitize run done")
