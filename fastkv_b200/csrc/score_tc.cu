@@ -388,6 +388,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     }
     tmem_wait_st();                                  // this thread's stores to TMEM are complete before pass 2 reads them
     if (et == 0 && ph == nph - 1) FKV_TRACE(4);
+    if (et == 0 && ph == 0 && nph > 1) FKV_TRACE(9);
 
     // ---------------- final (max, 1/sum) per row for every local pair ---------------------------
     // No grid barrier: a CTA only needs the partials of the CTAs that share its (b, h) pairs, and every
@@ -439,6 +440,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
     }
     named_bar(2, kEpiThreads);
     if (et == 0 && ph == nph - 1) FKV_TRACE(6);
+    if (et == 0 && ph == 0 && nph > 1) FKV_TRACE(10);
 
     // ---------------- pass 2: votes -> pool -> group sum -> score ------------------------------
     // every tile of the phase is still resident in TMEM; reading it frees the block for the next phase
@@ -541,6 +543,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant_
       t += kNumWG;
       while (t >= a.n_tiles) { t -= a.n_tiles; ++pair; }
     }
+    if (et == 0 && ph == 0 && nph > 1) FKV_TRACE(11);
     jbase += T;
     }                                                // phases
   }
@@ -729,13 +732,20 @@ int launch_score_tensor(const fkv_score_params& p, cudaStream_t s) {
     cudaMemcpy(host, trace_buf, sizeof(host), cudaMemcpyDeviceToHost);
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < pl.grid; ++c) if (host[c * 16] < t0) t0 = host[c * 16];
-    const char* names[9] = {"start", "setup", "first_acc", "last_p1_end", "last_flushed", "-", "last_colstat", "pass2_end", "exit"};
+    const char* names[12] = {"start", "setup", "first_acc", "-", "last_flushed", "-", "last_colstat", "pass2_end", "exit",
+                             "ph0_flushed", "ph0_colstat", "ph0_pass2_end"};
     fprintf(stderr, "[fkv trace] L=%d grid=%d pairs=%d ppp=%d phases=%d tiles/pair=%d stages=%d\n", p.L, pl.grid, pl.npairs, pl.ppp, pl.nph, pl.n_tiles, pl.nst);
-    for (int sidx = 0; sidx < 9; ++sidx) {
-      if (sidx == 5) continue;
+    for (int sidx = 0; sidx < (pl.nph > 1 ? 12 : 9); ++sidx) {
+      if (sidx == 5 || sidx == 3) continue;
       unsigned long long mn = ~0ull, mx = 0; double avg = 0;
       for (int c = 0; c < pl.grid; ++c) { unsigned long long v = host[c * 16 + sidx] - t0; if (v < mn) mn = v; if (v > mx) mx = v; avg += v; }
       fprintf(stderr, "[fkv trace] %-12s min %8.2f us  avg %8.2f us  max %8.2f us\n", names[sidx], mn / 1e3, avg / pl.grid / 1e3, mx / 1e3);
+    }
+    if (atoi(getenv("FKV_TC_TRACE")) >= 2) {            // CTA 0, tile by tile: TMA issue, operands landed (MMA issue), MMA committed
+      const unsigned long long* r = host + 256 * 16;
+      for (int m = 0; m < 64 && r[m]; ++m)
+        fprintf(stderr, "[fkv trace] cta0 tile %2d  tma %7.2f  mma %7.2f  committed %7.2f us\n", m, (r[m] - t0) / 1e3, (r[64 + m] - t0) / 1e3,
+                (r[128 + m] - t0) / 1e3);
     }
   }
   return rc_launch;
