@@ -91,3 +91,23 @@ def test_head_range_rejects_uneven_split():
     assert head_range(8, 3, 4) == (6, 8)
     with pytest.raises(ValueError):
         head_range(8, 0, 3)
+
+
+def test_exchange_modes_and_peer_region_sizes():
+    """Host-side pieces of the peer-memory exchange that need no GPU: mode validation, region sizing, and that a
+    single-rank shard never touches peer memory."""
+    from fastkv_b200.dist import HeadShard
+    from fastkv_b200.peer import PeerRegion
+    from fastkv_b200 import _lib as L
+    for mode in ("p2p", "gather", "reduce"):
+        assert HeadShard(exchange=mode).world_size == 1
+    with pytest.raises(ValueError):
+        HeadShard(exchange="broadcast")
+    assert PeerRegion.bytes_for(1, 8, 32760) == L.EXCHANGE_HEADER + 4 * 8 * 32760
+    assert PeerRegion.bytes_for(8, 8, 32760) == L.EXCHANGE_HEADER + 8 * 4 * 8 * 32760
+    shard = HeadShard(exchange="p2p")
+    s = torch.rand(1, 2, 64)
+    shard.begin_exchange(s)                              # world size 1: nothing to exchange, no region is created
+    assert shard.region is None and shard.exchange_scores(s) is s
+    with pytest.raises(RuntimeError):
+        PeerRegion(1024)                                 # needs an initialised process group (one rank per GPU)
