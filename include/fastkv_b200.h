@@ -286,7 +286,7 @@ typedef struct fkv_exchange_params {
   int64_t score_stride_b, score_stride_h;
   void* region[FKV_MAX_PEERS];        /* region[r] = rank r's peer region AS MAPPED IN THIS PROCESS          */
   size_t region_bytes;                /* >= FKV_EXCHANGE_HEADER_BYTES + B * world * heads_local * P * 4      */
-  int32_t max_ctas;                   /* 0 = library default                                                  */
+  int32_t max_ctas;                   /* 0 = library default; MUST be the same on every rank (receivers count push CTAs) */
   int32_t timeout_ms;                 /* 0 = 20 000                                                           */
 } fkv_exchange_params;
 int fkv_exchange_push(const fkv_exchange_params* p, void* stream);
