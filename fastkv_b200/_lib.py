@@ -14,7 +14,7 @@ import torch
 from . import _build
 
 # ---- enums (mirror include/fastkv_b200.h) -----------------------------------------------------
-ABI_VERSION = 5
+ABI_VERSION = 6
 BF16, F16, F32 = 0, 1, 2
 POOL_AVG, POOL_MAX = 0, 1
 MODE_FASTKV, MODE_SNAPKV, MODE_GEMFILTER = 0, 1, 2
@@ -24,6 +24,7 @@ EPOOL = -4
 ETIMEOUT = -11
 MAX_PEERS = 8
 EXCHANGE_HEADER = 256                      # FKV_EXCHANGE_HEADER_BYTES
+ALLREDUCE_HEADER = 2048                    # FKV_ALLREDUCE_HEADER_BYTES
 
 _DTYPES = {torch.bfloat16: BF16, torch.float16: F16, torch.float32: F32}
 _POOLS = {"avgpool": POOL_AVG, "maxpool": POOL_MAX}
@@ -133,13 +134,22 @@ class ExchangeParams(C.Structure):
     ]
 
 
+class AllreduceParams(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("rank", C.c_int32), ("world", C.c_int32), ("dtype", C.c_int32),
+        ("n", C.c_int64), ("data", C.c_void_p),
+        ("region", C.c_void_p * 8), ("region_bytes", C.c_size_t),
+        ("timeout_ms", C.c_int32),
+    ]
+
+
 EXPORTS = [
     "fkv_abi_version", "fkv_strerror", "fkv_workspace_bytes", "fkv_workspace_init", "fkv_workspace_status",
     "fkv_topk_workspace_bytes", "fkv_decode_workspace_bytes",
     "fkv_score_impl_name", "fkv_launch_count",
     "fkv_score", "fkv_topk", "fkv_gather_kv", "fkv_select_compact", "fkv_gather_rows", "fkv_decode_attn", "fkv_cache_append",
     "fkv_compress",
-    "fkv_exchange_push", "fkv_exchange_wait", "fkv_exchange_status",
+    "fkv_exchange_push", "fkv_exchange_wait", "fkv_exchange_status", "fkv_allreduce_sum",
     "fkv_peer_alloc", "fkv_peer_open", "fkv_peer_close", "fkv_peer_free",
 ]
 
@@ -181,7 +191,8 @@ def load():
                          ("fkv_select_compact", SelectCompactParams),
                          ("fkv_gather_rows", GatherRowsParams), ("fkv_decode_attn", DecodeAttnParams),
                          ("fkv_cache_append", CacheAppendParams), ("fkv_compress", CompressParams),
-                         ("fkv_exchange_push", ExchangeParams), ("fkv_exchange_wait", ExchangeParams)]:
+                         ("fkv_exchange_push", ExchangeParams), ("fkv_exchange_wait", ExchangeParams),
+                         ("fkv_allreduce_sum", AllreduceParams)]:
             fn = getattr(lib, name)
             fn.restype = C.c_int
             fn.argtypes = [C.POINTER(st), C.c_void_p]

@@ -308,6 +308,23 @@ int fkv_exchange_wait(const fkv_exchange_params* p, void* stream) {
   return launch_exchange_wait(*p, (cudaStream_t)stream);
 }
 
+int fkv_allreduce_sum(const fkv_allreduce_params* p, void* stream) {
+  if (!p || p->struct_size != sizeof(fkv_allreduce_params)) return FKV_EINVAL;
+  if (p->world < 1 || p->world > FKV_MAX_PEERS || p->rank < 0 || p->rank >= p->world || p->n < 1 || !p->data) return FKV_EINVAL;
+  if (p->dtype < FKV_BF16 || p->dtype > FKV_F32) return FKV_EDTYPE;
+  const size_t bytes = (size_t)p->n * dtype_size(p->dtype);
+  if (bytes % 16 || !aligned16(p->data)) return FKV_EALIGN;
+  for (int r = 0; r < p->world; ++r) {
+    if (!p->region[r]) return FKV_EINVAL;
+    if (!aligned16(p->region[r])) return FKV_EALIGN;
+  }
+  if (p->region_bytes < FKV_ALLREDUCE_HEADER_BYTES + 2 * (size_t)p->world * 256) return FKV_EWORKSPACE;
+  const size_t slot = ((p->region_bytes - FKV_ALLREDUCE_HEADER_BYTES) / (2 * (size_t)p->world)) & ~(size_t)255;
+  if (bytes > slot) return FKV_EWORKSPACE;
+  if (p->world == 1) return FKV_OK;                    // nothing to add
+  return launch_allreduce_sum(*p, (cudaStream_t)stream);
+}
+
 int fkv_exchange_status(const void* local_region, void* stream) {
   if (!local_region) return FKV_EINVAL;
   return exchange_status(local_region, (cudaStream_t)stream);

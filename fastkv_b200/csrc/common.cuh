@@ -179,4 +179,5 @@ size_t decode_workspace_bytes(int B, int Hq, int D, int max_seq_len);
 int launch_exchange_push(const fkv_exchange_params& p, cudaStream_t s);
 int launch_exchange_wait(const fkv_exchange_params& p, cudaStream_t s);
 int exchange_status(const void* region, cudaStream_t s);
+int launch_allreduce_sum(const fkv_allreduce_params& p, cudaStream_t s);
 }  // namespace fkv

@@ -205,6 +205,114 @@ int push_grid(const fkv_exchange_params& p) {
   return (int)(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
+// ---- small all-reduce (sum) over peer memory: see fkv_allreduce_sum in the public header -----------------------------
+constexpr int kArEpoch = 0, kArTicket = 1, kArErr = 2;
+constexpr int kArFlags = 64;          // u32 word index of flags[source][cta] (8 x 32 words)
+static_assert(kArFlags * 4 + FKV_MAX_PEERS * FKV_ALLREDUCE_MAX_CTAS * 4 <= FKV_ALLREDUCE_HEADER_BYTES, "all-reduce header layout");
+
+struct ArArgs {
+  char* data;
+  int64_t chunks;                     // 16-byte chunks
+  int dtype, rank, world;
+  size_t slot_bytes;
+  unsigned int* region[FKV_MAX_PEERS];
+  unsigned long long timeout_ns;
+};
+
+__device__ __forceinline__ uint4 ld_cg16(const void* p) {       // L2 only: the line may hold a two-exchanges-old value in L1
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+template <int DT>
+__device__ __forceinline__ void ar_accumulate(float* acc, const uint4& v) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  if constexpr (DT == FKV_F32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(w[i]);
+  } else if constexpr (DT == FKV_BF16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { acc[2 * i] += __uint_as_float(w[i] << 16); acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      acc[2 * i] += f.x; acc[2 * i + 1] += f.y;
+    }
+  }
+}
+
+template <int DT>
+__device__ __forceinline__ uint4 ar_pack(const float* acc) {
+  uint4 o;
+  uint32_t* w = reinterpret_cast<uint32_t*>(&o);
+  if constexpr (DT == FKV_F32) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = __float_as_uint(acc[i]);
+  } else if constexpr (DT == FKV_BF16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * i], acc[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const __half2 h = __floats2half2_rn(acc[2 * i], acc[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
+  }
+  return o;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kXThreads)
+allreduce_kernel(const __grid_constant__ ArArgs a) {
+  __shared__ unsigned int* region[FKV_MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < FKV_MAX_PEERS; ++r)
+    if (threadIdx.x == r) region[r] = a.region[r];
+  __syncthreads();
+  unsigned int* mine = region[a.rank];
+  const int tid = threadIdx.x;
+  const unsigned int e = ld_relaxed_gpu(mine + kArEpoch) + 1u;   // the last CTA out publishes e after every CTA has read this
+  const size_t slot_off = FKV_ALLREDUCE_HEADER_BYTES + (size_t)(e & 1u) * a.world * a.slot_bytes;
+  const int64_t per = (a.chunks + gridDim.x - 1) / gridDim.x;
+  const int64_t c0 = (int64_t)blockIdx.x * per, c1 = min(a.chunks, c0 + per);
+  // 1. this CTA's range of the local partial goes into slot [e & 1][rank] of every peer
+  for (int64_t c = c0 + tid; c < c1; c += kXThreads) {
+    const uint4 v = *reinterpret_cast<const uint4*>(a.data + c * 16);
+    for (int pp = 1; pp < a.world; ++pp) {
+      const int peer = (a.rank + pp) % a.world;
+      char* dst = reinterpret_cast<char*>(region[peer]) + slot_off + (size_t)a.rank * a.slot_bytes + c * 16;
+      asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  }
+  __syncthreads();
+  // 2. publish (one fence + one flag per peer), then wait for the same range from every peer
+  if (tid < a.world && tid != a.rank) {
+    fence_sys();
+    st_relaxed_sys(region[tid] + kArFlags + a.rank * FKV_ALLREDUCE_MAX_CTAS + blockIdx.x, e);
+    if (!wait_word(mine + kArFlags + tid * FKV_ALLREDUCE_MAX_CTAS + blockIdx.x, e, a.timeout_ns)) mine[kArErr] = 1u;
+    fence_sys();
+  }
+  __syncthreads();
+  // 3. sum in rank order, fp32, in place
+  for (int64_t c = c0 + tid; c < c1; c += kXThreads) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < a.world; ++r) {
+      const uint4 v = (r == a.rank) ? *reinterpret_cast<const uint4*>(a.data + c * 16)
+                                    : ld_cg16(reinterpret_cast<const char*>(mine) + slot_off + (size_t)r * a.slot_bytes + c * 16);
+      ar_accumulate<DT>(acc, v);
+    }
+    *reinterpret_cast<uint4*>(a.data + c * 16) = ar_pack<DT>(acc);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(mine + kArTicket, 1u);
+    if (prev == gridDim.x - 1) {
+      mine[kArTicket] = 0u;
+      __threadfence();
+      mine[kArEpoch] = e;
+    }
+  }
+}
+
 XArgs make_args(const fkv_exchange_params& p) {
   XArgs a{};
   a.score = p.score; a.sb = p.score_stride_b; a.sh = p.score_stride_h;
@@ -227,6 +335,24 @@ int launch_exchange_push(const fkv_exchange_params& p, cudaStream_t s) {
 int launch_exchange_wait(const fkv_exchange_params& p, cudaStream_t s) {
   const XArgs a = make_args(p);
   exchange_wait_kernel<<<1, 32, 0, s>>>(a);
+  FKV_LAUNCH_CHECK();
+  return FKV_OK;
+}
+
+int launch_allreduce_sum(const fkv_allreduce_params& p, cudaStream_t s) {
+  ArArgs a{};
+  const int es = dtype_size(p.dtype);
+  a.data = static_cast<char*>(p.data);
+  a.chunks = p.n * es / 16;
+  a.dtype = p.dtype; a.rank = p.rank; a.world = p.world;
+  a.slot_bytes = ((p.region_bytes - FKV_ALLREDUCE_HEADER_BYTES) / (2 * (size_t)p.world)) & ~(size_t)255;
+  for (int r = 0; r < p.world; ++r) a.region[r] = static_cast<unsigned int*>(p.region[r]);
+  a.timeout_ns = (unsigned long long)(p.timeout_ms > 0 ? p.timeout_ms : 20000) * 1000000ull;
+  int64_t want = (a.chunks + kXThreads - 1) / kXThreads;       // one chunk per thread up to 32 CTAs (same on every rank)
+  const int grid = (int)(want < 1 ? 1 : (want > FKV_ALLREDUCE_MAX_CTAS ? FKV_ALLREDUCE_MAX_CTAS : want));
+  if (p.dtype == FKV_F32) allreduce_kernel<FKV_F32><<<grid, kXThreads, 0, s>>>(a);
+  else if (p.dtype == FKV_BF16) allreduce_kernel<FKV_BF16><<<grid, kXThreads, 0, s>>>(a);
+  else allreduce_kernel<FKV_F16><<<grid, kXThreads, 0, s>>>(a);
   FKV_LAUNCH_CHECK();
   return FKV_OK;
 }

@@ -170,3 +170,28 @@ class PeerRegion:
     @staticmethod
     def bytes_for(b: int, heads_total: int, p: int) -> int:
         return L.EXCHANGE_HEADER + 4 * b * heads_total * p
+
+    # -- small all-reduce (a region used for this is used for nothing else) ---------------------------
+    @staticmethod
+    def allreduce_bytes_for(world_size: int, max_bytes: int) -> int:
+        return L.ALLREDUCE_HEADER + 2 * world_size * ((int(max_bytes) + 255) // 256 * 256)
+
+    def allreduce_capacity(self) -> int:
+        """Largest tensor (bytes) one ``all_reduce_`` call can sum through this region."""
+        return ((self.nbytes - L.ALLREDUCE_HEADER) // (2 * self.world_size)) // 256 * 256
+
+    def all_reduce_(self, t: torch.Tensor, *, timeout_ms: int = 0) -> torch.Tensor:
+        """In-place sum of ``t`` over the ranks (fkv_allreduce_sum: one kernel on the current stream, fp32 adds in rank
+        order — the same bits on every rank; CUDA-graph capturable)."""
+        L.require_cuda(t)
+        if not t.is_contiguous():
+            raise ValueError("fastkv_b200: all_reduce_ needs a contiguous tensor")
+        a = L.AllreduceParams()
+        a.struct_size = C.sizeof(L.AllreduceParams)
+        a.rank, a.world, a.dtype, a.n = self.rank, self.world_size, L.dtype_code(t.dtype), t.numel()
+        a.data = t.data_ptr()
+        for r, ptr in enumerate(self.ptrs):
+            a.region[r] = ptr
+        a.region_bytes, a.timeout_ms = self.nbytes, timeout_ms
+        L.check(L.load().fkv_allreduce_sum(C.byref(a), L.stream_ptr(self.device)))
+        return t

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FKV_ABI_VERSION 5
+#define FKV_ABI_VERSION 6
 
 /* Every `workspace` argument below is one kind of buffer: device memory, 256-byte aligned, passed ONCE through
  * fkv_workspace_init.  Its first FKV_WORKSPACE_HEADER_BYTES are persistent state owned by the library: 256 bytes
@@ -300,6 +300,29 @@ int fkv_peer_alloc(size_t bytes, void** ptr_out, unsigned char handle_out[64]);
 int fkv_peer_open(const unsigned char handle[64], void** ptr_out);
 int fkv_peer_close(void* mapped_ptr);
 int fkv_peer_free(void* ptr);
+
+/* ---- small all-reduce over peer memory (tensor-parallel DECODE steps of a head-sharded host) ---------------------- */
+/* Outside the §8 hot path proper, but what makes a KV-head-sharded decode step CUDA-graph capturable: the two hidden-state
+ * sums per layer of a tensor-parallel model are 8 KiB at batch 1 — pure latency — and NCCL cannot be captured on every
+ * stack.  One kernel: every rank stores its partial into a slot of every peer's region, fences, raises a per-(source,
+ * CTA) flag to the exchange number, waits for its peers' flags and adds the world partials in RANK ORDER in fp32 (the
+ * same bits on every rank), in place.  Two slots alternate by the exchange number kept in the region, so no handshake is
+ * needed and a captured graph replays without host state.  Same region ownership rules as fkv_exchange_*; this entry
+ * point wants its OWN region: [FKV_ALLREDUCE_HEADER_BYTES of counters and flags, zero-initialised once]
+ * [2 slots x world sources x slot bytes], slot bytes = (region_bytes - header) / (2 * world) rounded down to 256.      */
+#define FKV_ALLREDUCE_HEADER_BYTES 2048
+#define FKV_ALLREDUCE_MAX_CTAS 32
+typedef struct fkv_allreduce_params {
+  uint32_t struct_size;
+  int32_t rank, world;                /* world <= FKV_MAX_PEERS                                              */
+  int32_t dtype;                      /* FKV_BF16 / FKV_F16 / FKV_F32                                        */
+  int64_t n;                          /* elements; n * element size must be a multiple of 16 and fit a slot  */
+  void* data;                         /* in / out (device, 16-byte aligned): partial in, sum over ranks out  */
+  void* region[FKV_MAX_PEERS];        /* region[r] = rank r's all-reduce region AS MAPPED IN THIS PROCESS    */
+  size_t region_bytes;
+  int32_t timeout_ms;                 /* 0 = 20 000                                                           */
+} fkv_allreduce_params;
+int fkv_allreduce_sum(const fkv_allreduce_params* p, void* stream);
 
 /* ---- queries ----------------------------------------------------------------------------- */
 /* Bytes of scratch fkv_score / fkv_topk / fkv_compress need for these sizes (upper bound).     */

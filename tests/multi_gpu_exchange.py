@@ -111,6 +111,51 @@ def main():
     _, _, tsp1 = single.update_kv(k, q, v, None, 4, 0)
     torch.cuda.synchronize()
     assert torch.equal(tsp1, res["p2p"][2])             # identical to the unsharded selection
+    # the small all-reduce (tensor-parallel decode): == fp32 rank-order sum, same bits on every rank, graph replay, latency
+    n = 4096
+    ar = PeerRegion(PeerRegion.allreduce_bytes_for(world, 64 << 10))
+    gen = torch.Generator(device=dev).manual_seed(7)     # same stream of numbers on every rank -> every rank knows all partials
+    for it in range(4):
+        parts = [torch.randn(n, generator=gen, device=dev).bfloat16() for _ in range(world)]
+        want = torch.zeros(n, device=dev)
+        for p_ in parts:
+            want += p_.float()
+        mine = parts[rank].clone()
+        if it == 2 and rank == 0:
+            time.sleep(0.1)
+        ar.all_reduce_(mine)
+        torch.cuda.synchronize()
+        assert torch.equal(mine, want.bfloat16()), ("allreduce", it)
+    x = torch.randn(n, device=dev).bfloat16()
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        ar.all_reduce_(x)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=st):
+            for _ in range(64):
+                ar.all_reduce_(x)
+        dist.barrier(); torch.cuda.synchronize()
+        graph.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        graph.replay()
+        e1.record(st)
+        torch.cuda.synchronize()
+    y = torch.randn(n, device=dev).bfloat16()
+    for _ in range(5):
+        dist.all_reduce(y)
+    torch.cuda.synchronize()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(64):
+        dist.all_reduce(y)
+    e3.record()
+    torch.cuda.synchronize()
+    assert ar.status() == 0
+    report["allreduce_8KiB"] = {"peer_us_graph": round(e0.elapsed_time(e1) * 1e3 / 64, 2), "nccl_us_eager": round(e2.elapsed_time(e3) * 1e3 / 64, 2)}
+    del graph
+    ar.close()
     torch.cuda.synchronize()
     dist.barrier()
     if rank == 0:

@@ -31,10 +31,10 @@ def test_struct_sizes_match_c_layout():
     """ctypes mirrors must have the C sizes (checked against sizes compiled from the header)."""
     import subprocess, tempfile
     from fastkv_b200 import _lib
-    src = '#include <stdio.h>\n#include "fastkv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "fastkv_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(fkv_view4),sizeof(fkv_score_params),sizeof(fkv_topk_params),sizeof(fkv_gather_kv_params),' \
           'sizeof(fkv_gather_rows_params),sizeof(fkv_decode_attn_params),sizeof(fkv_cache_append_params),' \
-          'sizeof(fkv_compress_params),sizeof(fkv_select_compact_params),sizeof(fkv_exchange_params),(size_t)FKV_WORKSPACE_HEADER_BYTES);return 0;}\n'
+          'sizeof(fkv_compress_params),sizeof(fkv_select_compact_params),sizeof(fkv_exchange_params),sizeof(fkv_allreduce_params),(size_t)FKV_WORKSPACE_HEADER_BYTES);return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
         open(c, "w").write(src)
@@ -42,7 +42,7 @@ def test_struct_sizes_match_c_layout():
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [_lib.View4, _lib.ScoreParams, _lib.TopkParams, _lib.GatherKvParams, _lib.GatherRowsParams,
-               _lib.DecodeAttnParams, _lib.CacheAppendParams, _lib.CompressParams, _lib.SelectCompactParams, _lib.ExchangeParams]
+               _lib.DecodeAttnParams, _lib.CacheAppendParams, _lib.CompressParams, _lib.SelectCompactParams, _lib.ExchangeParams, _lib.AllreduceParams]
     assert sizes[:-1] == [ctypes.sizeof(m) for m in mirrors]
     assert sizes[-1] == _lib.WS_HEADER                         # the persistent region the Python side reserves
 
@@ -97,6 +97,17 @@ def test_null_and_bad_arguments_return_codes_without_a_gpu():
     xp.region_bytes = _lib.EXCHANGE_HEADER + 2 * 4 * 1024 * 4 - 1
     assert lib.fkv_exchange_push(ctypes.byref(xp), None) == -7      # region too small for the gathered rows
     assert lib.fkv_exchange_status(None, None) == -1
+    ar = _lib.AllreduceParams()
+    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -1       # struct_size guard
+    ar.struct_size = ctypes.sizeof(_lib.AllreduceParams)
+    ar.rank, ar.world, ar.dtype, ar.n, ar.data = 0, 2, 0, 4096, 4096
+    ar.region[0], ar.region[1] = 8192, 16384
+    ar.region_bytes = _lib.ALLREDUCE_HEADER + 2 * 2 * 4096
+    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -7       # 8 KiB of bf16 do not fit a 4 KiB slot
+    ar.n = 4100
+    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -6       # byte count not a multiple of 16
+    ar.n, ar.dtype = 4096, 7
+    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -2
     assert b"peer" in lib.fkv_strerror(_lib.ETIMEOUT)
     sp.D, sp.kernel_size, sp.hist_slot = 128, 7, 3
     sp.pooling, sp.window_size, sp.h1 = 0, 8, 2

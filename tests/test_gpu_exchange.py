@@ -112,6 +112,62 @@ def test_missing_peer_times_out_instead_of_hanging():
     assert regions[0].status() == L.ETIMEOUT
 
 
+@pytest.mark.parametrize("world,n,dtype", [(2, 4096, torch.bfloat16), (4, 4096, torch.bfloat16), (8, 8 * 4096, torch.bfloat16),
+                                           (2, 1000 * 8, torch.float16), (4, 40000, torch.float32)])
+def test_peer_allreduce_sums_in_rank_order_on_every_rank(world, n, dtype):
+    """fkv_allreduce_sum with N "ranks" on one device: fp32 adds in rank order, identical bits on all ranks, graph replay."""
+    from fastkv_b200.peer import PeerRegion
+    dev = torch.device("cuda", 0)
+    regions = PeerRegion.local_group(world, PeerRegion.allreduce_bytes_for(world, n * 4), dev)
+    streams = [torch.cuda.Stream(dev) for _ in range(world)]
+    g = torch.Generator(device=dev).manual_seed(9)
+    bufs = [torch.empty(n, dtype=dtype, device=dev) for _ in range(world)]
+
+    def fill():
+        parts = [torch.randn(n, generator=g, device=dev).to(dtype) for _ in range(world)]
+        for b_, p_ in zip(bufs, parts):
+            b_.copy_(p_)
+        acc = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p_ in parts:                                 # rank order, fp32
+            acc += p_.float()
+        return acc.to(dtype)
+
+    def launch_all():
+        for r, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                regions[r].all_reduce_(bufs[r], timeout_ms=5000)
+
+    for it in range(3):                                  # both slots, several epochs
+        want = fill()
+        torch.cuda.synchronize()
+        launch_all()
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert torch.equal(bufs[r], want), (it, r)
+    # one graph holding all ranks' kernels (fork / join), replayed with fresh inputs: no host-side state
+    main = torch.cuda.Stream(dev)
+    with torch.cuda.stream(main):
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=main):
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for r, st in enumerate(streams):
+                st.wait_event(fork)
+                with torch.cuda.stream(st):
+                    regions[r].all_reduce_(bufs[r], timeout_ms=5000)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                main.wait_event(ev)
+        for it in range(3):
+            want = fill()
+            torch.cuda.synchronize()
+            graph.replay()
+            torch.cuda.synchronize()
+            for r in range(world):
+                assert torch.equal(bufs[r], want), ("graph", it, r)
+    assert all(reg.status() == 0 for reg in regions)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_two_process_exchange():
     env = dict(os.environ, PYTHONPATH=ROOT)

@@ -40,13 +40,19 @@ def build_model(kind, layers=None, dtype=torch.bfloat16, device="cuda", tp=1):
     return model.eval()
 
 
-def add_tp_allreduce(model):
+def add_tp_allreduce(model, peer=None):
     """Row-parallel projections: sum the partial outputs of o_proj and down_proj over the ranks (2 all-reduces per
-    layer, library NCCL; outside the hot path).  Embedding, norms and lm_head are replicated."""
+    layer; outside the hot path).  Embedding, norms and lm_head are replicated.  Prefill-sized tensors go through library
+    NCCL; with ``peer`` (a PeerRegion) the small decode-step sums use the library's own peer-memory all-reduce
+    (fkv_allreduce_sum), which can be captured in the decode graph."""
     import torch.distributed as dist
+    cap = peer.allreduce_capacity() if peer is not None else 0
 
     def hook(_mod, _inp, out):
-        dist.all_reduce(out)
+        if peer is not None and out.numel() * out.element_size() <= cap and out.is_contiguous() and (out.numel() * out.element_size()) % 16 == 0:
+            peer.all_reduce_(out)
+        else:
+            dist.all_reduce(out)
         return out
 
     for layer in model.model.layers:
@@ -69,8 +75,15 @@ def run(args):
         if not dist.is_initialized():
             dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     model = build_model(args.model, layers=args.layers, tp=tp)
+    peer_ar = None
     if tp > 1:
-        add_tp_allreduce(model)
+        if os.environ.get("FKV_PEER_ALLREDUCE", "1") != "0":
+            from fastkv_b200.peer import PeerRegion
+            try:
+                peer_ar = PeerRegion(PeerRegion.allreduce_bytes_for(tp, 256 << 10))
+            except RuntimeError as e:
+                print(f"[model_bench] no peer memory ({e}); decode all-reduces stay on NCCL (eager)", file=sys.stderr)
+        add_tp_allreduce(model, peer_ar)
     a = types.SimpleNamespace(method=args.method, max_capacity_prompts=args.capacity, window_size=8, kernel_size=7,
                               pooling="avgpool", retain_rate=0.1, eviction_mode="constant", tsp_len=args.tsp_len,
                               tsp_rate=0.2, tsp_idx=tsp_idx, merge=None)
@@ -98,7 +111,7 @@ def run(args):
             cache = out.past_key_values
             tok = out.logits[:, -1, :].argmax(dim=-1, keepdim=True)
             s2, e2 = ev(), ev()
-            if args.graph and args.method != "fullkv" and tp == 1:   # (NCCL all-reduces inside a captured graph hang on this stack)
+            if args.graph and args.method != "fullkv" and (tp == 1 or peer_ar is not None):   # (NCCL inside a captured graph hangs on this stack; the peer-memory all-reduce is capturable)
                 gd = patch.GraphedDecode(model, cache, tok)          # 2 eager steps + capture (untimed)
                 n_timed = args.genlen - 1 - 2
                 s2.record()
@@ -128,7 +141,8 @@ def run(args):
         "n_gpus": tp, "parallelism": f"tp{tp} (kv-head-sharded compressor, 2 hidden all-reduces per layer)" if tp > 1 else "none",
         "model": args.model, "layers": args.layers or (32 if args.model == "llama" else 36), "method": args.method,
         "ctx": args.ctx, "batch": args.batch, "capacity": args.capacity, "tsp_len": args.tsp_len, "tsp_idx": tsp_idx,
-        "genlen": args.genlen, "tsp_layer_rows": "all" if getattr(args, "dense_tsp_layer", False) else "kept only", "decode_cuda_graph": bool(args.graph and args.method != "fullkv" and tp == 1), "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
+        "genlen": args.genlen, "tsp_layer_rows": "all" if getattr(args, "dense_tsp_layer", False) else "kept only", "decode_cuda_graph": bool(args.graph and args.method != "fullkv" and (tp == 1 or peer_ar is not None)),
+        "decode_allreduce": ("peer memory (fkv_allreduce_sum)" if peer_ar is not None else "nccl") if tp > 1 else None, "ttft_ms": round(ttft, 2), "decode_ms_per_token": round(dec / max(args.genlen - 1, 1), 3),
         "decode_tok_s": round(args.batch * (args.genlen - 1) / (dec / 1e3), 1),
         "reference_throughput_tok_s": round((args.genlen - 1) / ((ttft + dec) / 1e3), 2),   # benchmark/e2e.py:183 definition
         "peak_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 2), "data": "random-init weights, all-ones ids",
@@ -138,6 +152,8 @@ def run(args):
     if tp > 1:
         import torch.distributed as dist
         torch.cuda.synchronize()
+        if peer_ar is not None:
+            peer_ar.close()
         dist.barrier()
         dist.destroy_process_group()
     return line
