@@ -320,7 +320,7 @@ int fkv_allreduce_sum(const fkv_allreduce_params* p, void* stream) {
   }
   if (p->region_bytes < FKV_ALLREDUCE_HEADER_BYTES + 2 * (size_t)p->world * 256) return FKV_EWORKSPACE;
   const size_t slot = ((p->region_bytes - FKV_ALLREDUCE_HEADER_BYTES) / (2 * (size_t)p->world)) & ~(size_t)255;
-  if (bytes > slot) return FKV_EWORKSPACE;
+  if (bytes > slot / 2) return FKV_EWORKSPACE;         // (half a slot: the other half holds the tagged lines of small sums)
   if (p->world == 1) return FKV_OK;                    // nothing to add
   return launch_allreduce_sum(*p, (cudaStream_t)stream);
 }

@@ -6,9 +6,11 @@
 //                          every rank's region -> one release of a per-source DATA flag per peer
 //   exchange_wait_kernel   acquires the peers' DATA flags; the consumer (fkv_topk, nsum = all heads) follows on
 //                          the same stream
+//   allreduce_kernel /     the small in-place sum of tensor-parallel decode steps over the same kind of region
+//   allreduce_ll_kernel    (fkv_allreduce_sum; second half of this file)
 // Everything is stream-ordered device work: capturable in a CUDA graph, no host round trip, no NCCL.
 //
-// Region header (u32 words; FKV_EXCHANGE_HEADER_BYTES = 256):
+// Region header of the score exchange (u32 words; FKV_EXCHANGE_HEADER_BYTES = 256):
 //   [0]        number of exchanges completed on the owner (bumped by its wait kernel)             (owner only)
 //   [2]        error word: 1 = a handshake / data wait timed out                                  (owner only)
 //   [8 + s]    READY word written by rank s: "s has entered push number e" (=> s consumed exchange e - 1)
@@ -279,7 +281,7 @@ allreduce_kernel(const __grid_constant__ ArArgs a) {
     const uint4 v = *reinterpret_cast<const uint4*>(a.data + c * 16);
     for (int pp = 1; pp < a.world; ++pp) {
       const int peer = (a.rank + pp) % a.world;
-      char* dst = reinterpret_cast<char*>(region[peer]) + slot_off + (size_t)a.rank * a.slot_bytes + c * 16;
+      char* dst = reinterpret_cast<char*>(region[peer]) + slot_off + (size_t)a.rank * a.slot_bytes + (a.slot_bytes >> 1) + c * 16;
       asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
   }
@@ -297,9 +299,80 @@ allreduce_kernel(const __grid_constant__ ArArgs a) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int r = 0; r < a.world; ++r) {
       const uint4 v = (r == a.rank) ? *reinterpret_cast<const uint4*>(a.data + c * 16)
-                                    : ld_cg16(reinterpret_cast<const char*>(mine) + slot_off + (size_t)r * a.slot_bytes + c * 16);
+                                    : ld_cg16(reinterpret_cast<const char*>(mine) + slot_off + (size_t)r * a.slot_bytes + (a.slot_bytes >> 1) + c * 16);
       ar_accumulate<DT>(acc, v);
     }
+    *reinterpret_cast<uint4*>(a.data + c * 16) = ar_pack<DT>(acc);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int prev = atomicAdd(mine + kArTicket, 1u);
+    if (prev == gridDim.x - 1) {
+      mine[kArTicket] = 0u;
+      __threadfence();
+      mine[kArEpoch] = e;
+    }
+  }
+}
+
+// Low-latency variant for the sizes decode steps actually sum (<= 64 KiB): no fence and no separate flag.  Every 16-byte
+// store carries 8 bytes of payload and the exchange number twice ({d0, e, d1, e}: a 16-byte store lands as a whole), the
+// receiver spins on the line itself until both tags read e — one NVLink one-way latency instead of a fence round trip
+// plus a flag.  Tagged lines take 2 x the tensor's bytes and live in the FIRST half of a slot, the plain rows of the
+// fence + flag kernel in the second half, so the two never overlay (a stale payload word can therefore never be taken for a
+// tag); tags of older exchanges (e - 2 in the same slot) never match.
+__device__ __forceinline__ void st_ll16(void* p, uint32_t d0, uint32_t d1, uint32_t e) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(d0), "r"(e), "r"(d1), "r"(e) : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll16(const void* p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
+template <int DT>
+__global__ void __launch_bounds__(kXThreads)
+allreduce_ll_kernel(const __grid_constant__ ArArgs a) {
+  __shared__ unsigned int* region[FKV_MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < FKV_MAX_PEERS; ++r)
+    if (threadIdx.x == r) region[r] = a.region[r];
+  __syncthreads();
+  unsigned int* mine = region[a.rank];
+  const int tid = threadIdx.x;
+  const unsigned int e = ld_relaxed_gpu(mine + kArEpoch) + 1u;
+  const size_t slot_off = FKV_ALLREDUCE_HEADER_BYTES + (size_t)(e & 1u) * a.world * a.slot_bytes;
+  const int64_t c = (int64_t)blockIdx.x * kXThreads + tid;       // one 16-byte chunk per thread (the launcher sizes the grid)
+  const bool active = c < a.chunks;
+  uint4 own = make_uint4(0u, 0u, 0u, 0u);
+  if (active) {
+    own = *reinterpret_cast<const uint4*>(a.data + c * 16);
+    for (int pp = 1; pp < a.world; ++pp) {
+      const int peer = (a.rank + pp) % a.world;
+      char* dst = reinterpret_cast<char*>(region[peer]) + slot_off + (size_t)a.rank * a.slot_bytes + c * 32;
+      st_ll16(dst, own.x, own.y, e);
+      st_ll16(dst + 16, own.z, own.w, e);
+    }
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool timed_out = false;
+    for (int r = 0; r < a.world; ++r) {                          // rank order
+      uint4 v = own;
+      if (r != a.rank) {
+        const char* src = reinterpret_cast<const char*>(mine) + slot_off + (size_t)r * a.slot_bytes + c * 32;
+        uint4 lo = ld_ll16(src), hi = ld_ll16(src + 16);
+        if (lo.y != e || lo.w != e || hi.y != e || hi.w != e) {
+          const unsigned long long t0 = now_ns();
+          int spins = 0;
+          do {
+            lo = ld_ll16(src); hi = ld_ll16(src + 16);
+            if ((++spins & 63) == 0 && now_ns() - t0 > a.timeout_ns) { timed_out = true; break; }
+          } while (lo.y != e || lo.w != e || hi.y != e || hi.w != e);
+        }
+        v = make_uint4(lo.x, lo.z, hi.x, hi.z);
+      }
+      ar_accumulate<DT>(acc, v);
+    }
+    if (timed_out) mine[kArErr] = 1u;
     *reinterpret_cast<uint4*>(a.data + c * 16) = ar_pack<DT>(acc);
   }
   __syncthreads();
@@ -349,6 +422,16 @@ int launch_allreduce_sum(const fkv_allreduce_params& p, cudaStream_t s) {
   for (int r = 0; r < p.world; ++r) a.region[r] = static_cast<unsigned int*>(p.region[r]);
   a.timeout_ns = (unsigned long long)(p.timeout_ms > 0 ? p.timeout_ms : 20000) * 1000000ull;
   int64_t want = (a.chunks + kXThreads - 1) / kXThreads;       // one chunk per thread up to 32 CTAs (same on every rank)
+  static const bool no_ll = getenv("FKV_AR_NO_LL") != nullptr;  // experiments: always take the fence + flag kernel
+  const size_t bytes = (size_t)a.chunks * 16;
+  if (!no_ll && bytes <= (64u << 10) && 2 * bytes <= (a.slot_bytes >> 1)) {   // decode-step sizes: tagged 16-byte lines, no fence
+    const int g = (int)want;                                    // <= 16 CTAs for 64 KiB
+    if (p.dtype == FKV_F32) allreduce_ll_kernel<FKV_F32><<<g, kXThreads, 0, s>>>(a);
+    else if (p.dtype == FKV_BF16) allreduce_ll_kernel<FKV_BF16><<<g, kXThreads, 0, s>>>(a);
+    else allreduce_ll_kernel<FKV_F16><<<g, kXThreads, 0, s>>>(a);
+    FKV_LAUNCH_CHECK();
+    return FKV_OK;
+  }
   const int grid = (int)(want < 1 ? 1 : (want > FKV_ALLREDUCE_MAX_CTAS ? FKV_ALLREDUCE_MAX_CTAS : want));
   if (p.dtype == FKV_F32) allreduce_kernel<FKV_F32><<<grid, kXThreads, 0, s>>>(a);
   else if (p.dtype == FKV_BF16) allreduce_kernel<FKV_BF16><<<grid, kXThreads, 0, s>>>(a);

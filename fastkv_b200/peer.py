@@ -174,11 +174,12 @@ class PeerRegion:
     # -- small all-reduce (a region used for this is used for nothing else) ---------------------------
     @staticmethod
     def allreduce_bytes_for(world_size: int, max_bytes: int) -> int:
-        return L.ALLREDUCE_HEADER + 2 * world_size * ((int(max_bytes) + 255) // 256 * 256)
+        """Region size whose slots take tensors of up to ``max_bytes`` (a tensor may use half a slot)."""
+        return L.ALLREDUCE_HEADER + 2 * world_size * 2 * ((int(max_bytes) + 255) // 256 * 256)
 
     def allreduce_capacity(self) -> int:
         """Largest tensor (bytes) one ``all_reduce_`` call can sum through this region."""
-        return ((self.nbytes - L.ALLREDUCE_HEADER) // (2 * self.world_size)) // 256 * 256
+        return (((self.nbytes - L.ALLREDUCE_HEADER) // (2 * self.world_size)) // 256 * 256) // 2
 
     def all_reduce_(self, t: torch.Tensor, *, timeout_ms: int = 0) -> torch.Tensor:
         """In-place sum of ``t`` over the ranks (fkv_allreduce_sum: one kernel on the current stream, fp32 adds in rank

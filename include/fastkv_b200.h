@@ -309,14 +309,16 @@ int fkv_peer_free(void* ptr);
  * same bits on every rank), in place.  Two slots alternate by the exchange number kept in the region, so no handshake is
  * needed and a captured graph replays without host state.  Same region ownership rules as fkv_exchange_*; this entry
  * point wants its OWN region: [FKV_ALLREDUCE_HEADER_BYTES of counters and flags, zero-initialised once]
- * [2 slots x world sources x slot bytes], slot bytes = (region_bytes - header) / (2 * world) rounded down to 256.      */
+ * [2 slots x world sources x slot bytes], slot bytes = (region_bytes - header) / (2 * world) rounded down to 256; a
+ * tensor may take up to HALF a slot (sums of <= 64 KiB that fit a quarter travel as tagged 16-byte lines — payload and
+ * exchange number in one store, no fence — in the other half).                                                      */
 #define FKV_ALLREDUCE_HEADER_BYTES 2048
 #define FKV_ALLREDUCE_MAX_CTAS 32
 typedef struct fkv_allreduce_params {
   uint32_t struct_size;
   int32_t rank, world;                /* world <= FKV_MAX_PEERS                                              */
   int32_t dtype;                      /* FKV_BF16 / FKV_F16 / FKV_F32                                        */
-  int64_t n;                          /* elements; n * element size must be a multiple of 16 and fit a slot  */
+  int64_t n;                          /* elements; n * element size: a multiple of 16, at most half a slot   */
   void* data;                         /* in / out (device, 16-byte aligned): partial in, sum over ranks out  */
   void* region[FKV_MAX_PEERS];        /* region[r] = rank r's all-reduce region AS MAPPED IN THIS PROCESS    */
   size_t region_bytes;

@@ -102,8 +102,8 @@ def test_null_and_bad_arguments_return_codes_without_a_gpu():
     ar.struct_size = ctypes.sizeof(_lib.AllreduceParams)
     ar.rank, ar.world, ar.dtype, ar.n, ar.data = 0, 2, 0, 4096, 4096
     ar.region[0], ar.region[1] = 8192, 16384
-    ar.region_bytes = _lib.ALLREDUCE_HEADER + 2 * 2 * 4096
-    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -7       # 8 KiB of bf16 do not fit a 4 KiB slot
+    ar.region_bytes = _lib.ALLREDUCE_HEADER + 2 * 2 * 8192
+    assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -7       # 8 KiB of bf16 do not fit half of an 8 KiB slot
     ar.n = 4100
     assert lib.fkv_allreduce_sum(ctypes.byref(ar), None) == -6       # byte count not a multiple of 16
     ar.n, ar.dtype = 4096, 7
