@@ -206,3 +206,71 @@ def test_generate_path_positions_follow_the_true_length(patched, with_mask, own_
     assert [p[-1] for p in seen[1:]] == list(range(n, n + new - 1)), seen[1:]
     if own_cache:
         assert cache.get_seq_length() == 16 + new - 1 and cache.true_length == n + new - 1
+
+
+class _KeepEveryThird:
+    """Compressor double with a TSP selection (CPU): keeps the first C-W rows + window in the cache and propagates every
+    third token plus the window — enough to drive the glue of the TSP layer without a GPU."""
+
+    def __init__(self, tsp_layer, capacity=16, window=4):
+        self.tsp_layer, self.c, self.w = tsp_layer, capacity, window
+
+    def update_kv(self, k, q, v, attention_mask, groups, layer_idx=None):
+        n = k.shape[2]
+        if n < self.c:
+            return k, v, None
+        sel = lambda x: torch.cat([x[:, :, :self.c - self.w], x[:, :, -self.w:]], dim=2).contiguous()
+        tsp = None
+        if self.tsp_layer:
+            keep = torch.cat([torch.arange(0, n - self.w, 3), torch.arange(n - self.w, n)])
+            tsp = keep.unsqueeze(0).expand(k.shape[0], -1).contiguous()
+        return sel(k), sel(v), tsp
+
+
+@pytest.mark.parametrize("impl,window", [("sdpa", None), ("eager", None), ("eager", 20)])
+def test_tsp_layer_row_pruning_matches_the_reference_order_on_cpu(patched, monkeypatch, impl, window):
+    """The TSP layer computes attention / MLP rows for the kept tokens only (default) or for all tokens with the gather
+    after the MLP (``fastkv_sparse_tsp_layer = False``, the reference's order, llama_model.py:252-259): same hidden states,
+    same propagated positions.  ``ops.gather_rows`` is the CUDA kernel: a torch double stands in for it here."""
+    from fastkv_b200 import ops, patch as P
+
+    def gather_rows_double(hidden, idx, position_ids=None):
+        out = hidden.gather(1, idx[..., None].expand(-1, -1, hidden.shape[-1]))
+        if position_ids is None:
+            return out
+        return out, position_ids.expand(hidden.shape[0], -1).gather(1, idx)
+
+    monkeypatch.setattr(ops, "gather_rows", gather_rows_double)
+    if window is not None:
+        from transformers import MistralConfig, MistralForCausalLM
+        P.replace_mistral("fastkv")
+        cfg = MistralConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, num_key_value_heads=1,
+                            head_dim=64, vocab_size=97, max_position_embeddings=512, sliding_window=window, attn_implementation=impl)
+        make = lambda: MistralForCausalLM(cfg).eval()
+    else:
+        from transformers import LlamaConfig, LlamaForCausalLM
+        cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=3, num_attention_heads=2, num_key_value_heads=1,
+                          head_dim=64, vocab_size=97, max_position_embeddings=512, attn_implementation=impl)
+        make = lambda: LlamaForCausalLM(cfg).eval()
+    ids = torch.randint(1, 97, (2, 50), generator=torch.Generator().manual_seed(5))
+    outs = []
+    try:
+        for sparse in (False, True):
+            torch.manual_seed(0)
+            model = make()
+            model.config.fastkv_sparse_tsp_layer = sparse
+            patched.set_model(model, _args())
+            for i, layer in enumerate(model.model.layers):
+                layer.self_attn.kv_cluster = _KeepEveryThird(tsp_layer=(i == 1))
+            with torch.no_grad():
+                out = model.model(ids, use_cache=True)
+            assert (model.model.layers[1].self_attn.rows_kept is not None) == sparse
+            assert model.model.layers[1].new_position_ids.shape == (2, 16 + 4)
+            outs.append((out.last_hidden_state, model.model.layers[1].new_position_ids.clone(),
+                         out.past_key_values.get_seq_length(2)))
+    finally:
+        if window is not None:
+            P.replace_mistral("fullkv")
+    (h0, p0, n0), (h1, p1, n1) = outs
+    assert torch.equal(p0, p1) and n0 == n1
+    assert torch.allclose(h0, h1, atol=2e-5, rtol=1e-4), (h0 - h1).abs().max()
